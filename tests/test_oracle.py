@@ -1,0 +1,162 @@
+"""CPU tests: the oracle against itself, the golden vectors and the reference-side known answers.
+(Go tests pin nothing for this path; these are the pins that exist.)"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_gray, GOLDEN
+
+sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _cases():
+    rng = np.random.default_rng(7)
+    out = []
+    for i in range(48):
+        W = int(rng.integers(1, 48)); H = int(rng.integers(1, 36))
+        B = int(rng.integers(1, 32)); D = int(rng.integers(1, 80))
+        kind = i % 4
+        if kind == 0:
+            L = rng.integers(0, 256, (H, W), dtype=np.uint8); R = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        elif kind == 1:     # flat: every candidate ties
+            L = np.full((H, W), 9, np.uint8); R = np.full((H, W), 9, np.uint8)
+        elif kind == 2:     # few grey levels: tie heavy
+            L = rng.integers(0, 3, (H, W), dtype=np.uint8); R = rng.integers(0, 3, (H, W), dtype=np.uint8)
+        else:               # all-zero left
+            L = np.zeros((H, W), np.uint8); R = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        out.append((L, R, B, D))
+    return out
+
+
+def test_literal_equals_box_equals_numpy(oracle):
+    from oracle import sad_numpy as N
+    for L, R, B, D in _cases():
+        H, W = L.shape
+        a = oracle.region_literal(L, R, (0, 0, W, H), B, D)
+        assert np.array_equal(a, oracle.frame_box(L, R, B, D)), (W, H, B, D)
+        assert np.array_equal(a, N.box_numpy(L, R, B, D)), (W, H, B, D)
+
+
+def test_pure_python_transliteration(oracle):
+    from oracle import sad_numpy as N
+    for L, R, B, D in _cases()[:8]:
+        H, W = L.shape
+        assert np.array_equal(N.literal_py(L, R, B, D), oracle.region_literal(L, R, (0, 0, W, H), B, D))
+
+
+def test_early_exit_is_result_neutral(oracle):
+    for L, R, B, D in _cases()[:16]:
+        H, W = L.shape
+        assert np.array_equal(oracle.region_literal(L, R, (0, 0, W, H), B, D, early_exit=True),
+                              oracle.region_literal(L, R, (0, 0, W, H), B, D, early_exit=False))
+
+
+def test_regions_and_row_ranges_do_not_change_pixels(oracle):
+    rng = np.random.default_rng(3)
+    L = rng.integers(0, 256, (40, 60), dtype=np.uint8); R = rng.integers(0, 256, (40, 60), dtype=np.uint8)
+    full = oracle.frame_box(L, R, 7, 20)
+    assert np.array_equal(oracle.region_literal(L, R, (13, 5, 47, 31), 7, 20), full[5:31, 13:47])
+    assert np.array_equal(oracle.frame_box(L, R, 7, 20, 11, 29), full[11:29])
+    assert np.array_equal(oracle.frame_literal_mt(L, R, 7, 20, threads=3), full)
+
+
+def test_even_block_behaves_as_next_odd(oracle):
+    rng = np.random.default_rng(5)
+    L = rng.integers(0, 256, (30, 50), dtype=np.uint8); R = rng.integers(0, 256, (30, 50), dtype=np.uint8)
+    assert np.array_equal(oracle.frame_box(L, R, 16, 32), oracle.frame_box(L, R, 17, 32))
+
+
+def test_left_border_is_zero_and_range_is_clamped(oracle):
+    rng = np.random.default_rng(6)
+    L = rng.integers(0, 256, (20, 64), dtype=np.uint8); R = rng.integers(0, 256, (20, 64), dtype=np.uint8)
+    B, D = 9, 32
+    out = oracle.region_literal(L, R, (0, 0, 64, 20), B, D)
+    assert not out[:, :B // 2].any()
+    x = np.arange(64)
+    assert (out.astype(int) <= (np.clip(x - B // 2, 0, D) * 255) // D).all()
+
+
+def test_golden_sha_pins(oracle, manifest):
+    for tag, rec in manifest["pairs"].items():
+        L = load_gray(f"L_{tag}_gray.png"); R = load_gray(f"R_{tag}_gray.png")
+        assert sha(L) == rec["left_sha256"] and sha(R) == rec["right_sha256"]
+        out = oracle.frame_box(L, R, 9, 64)
+        assert sha(out) == rec["b9_d64_sha256"] == manifest["survey_pins"][f"{tag}_b9_d64"]
+        assert np.array_equal(out, load_gray(f"disp_{tag}_b9_d64.png"))
+    L = load_gray("L_00001_gray.png"); R = load_gray("R_00001_gray.png")
+    assert sha(oracle.frame_box(L, R, 16, 64)) == manifest["survey_pins"]["00001_b16_d64"]
+
+
+def test_golden_literal_rows_on_real_pair(oracle):
+    L = load_gray("L_00001_gray.png"); R = load_gray("R_00001_gray.png")
+    exp = load_gray("disp_00001_b9_d64.png")
+    got = oracle.frame_literal_mt(L, R, 9, 64, threads=os.cpu_count() or 1, y0=100, y1=112)
+    assert np.array_equal(got, exp[100:112])
+
+
+def test_fpga_known_answers_interior(oracle):
+    """hardware/mems/exp_disp_p.mem (hardware/test.py:262-294) and hardware/exp_disp.mem
+    (hardware/sad.c) agree with the Go semantics on x in [71,121)."""
+    v = np.load(os.path.join(GOLDEN, "fpga_vectors.npz"))
+    for k in range(4):
+        got = oracle.frame_box(v["L"][k], v["R"][k], 15, 64)
+        exp = (v["exp_disp_p"][k].astype(int) * 255 // 64).astype(np.uint8)
+        assert np.array_equal(got[:, 71:121], exp[:, 71:121]), k
+    got = oracle.frame_box(v["L"][1], v["R"][1], 15, 64)
+    exp = (v["exp_disp_c_patch1"].astype(int) * 255 // 64).astype(np.uint8)
+    assert np.array_equal(got[7:121, 71:121], exp[7:121, 71:121])
+
+
+def test_reference_c_generator_on_random_patches(oracle):
+    """oracle/_ref/hw_sad = /root/reference/hardware/sad.c compiled unmodified, run on random
+    128x128 patches by tests/golden/make_golden.py; same interior rectangle."""
+    v = np.load(os.path.join(GOLDEN, "fpga_vectors.npz"))
+    for k in range(v["hw_sad_L"].shape[0]):
+        got = oracle.frame_box(v["hw_sad_L"][k], v["hw_sad_R"][k], 15, 64)
+        exp = (v["hw_sad_out"][k].astype(int) * 255 // 64).astype(np.uint8)
+        assert np.array_equal(got[7:121, 71:121], exp[7:121, 71:121]), k
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/testdata/L_00001.png"), reason="reference tree absent")
+def test_go_exact_loader_against_reference_files(manifest):
+    from oracle.go_image import load_png
+    L = load_png("/root/reference/testdata/L_00001.png")
+    assert sha(L) == manifest["pairs"]["00001"]["left_sha256"]
+    assert not load_png("/root/reference/testdata/im0.png", "loadpng").any()   # gray.go:35-37 bug
+    assert sha(load_png("/root/reference/testdata/im0.png", "intended")) == manifest["cfg2"]["left_sha256"]
+
+
+def test_cfg2_pin(oracle, manifest):
+    L = load_gray("im0_intended_gray.png"); R = load_gray("im1_intended_gray.png")
+    assert sha(L) == manifest["cfg2"]["left_sha256"]
+    exp = load_gray("disp_im0_im1_intended_b15_d256.png")
+    assert sha(exp) == manifest["survey_pins"]["im0_im1_intended_b15_d256"]
+    got = oracle.frame_box(L, R, 15, 256, 500, 520)
+    assert np.array_equal(got, exp[500:520])
+
+
+def test_chunk_planners_and_assemble_bug(oracle):
+    # RunSad tiling, pkg/despair/sad.go:128-153
+    rects = oracle.run_sad_chunks(640, 480, 8)
+    cover = np.zeros((480, 640), int)
+    for x0, y0, x1, y1 in rects:
+        cover[y0:y1, x0:x1] += 1
+    assert (cover == 1).all()
+    # OutputCamera bands, output.go:172-187: 480 rows -> 3-row bands, 160 chunks
+    bands = oracle.output_camera_chunks(640, 480)
+    assert len(bands) == 160 and bands[0] == (0, 0, 640, 3)
+    # AssembleDisparityMap drops the last-arriving chunk (sad.go:179-184)
+    rng = np.random.default_rng(1)
+    L = rng.integers(0, 256, (24, 40), dtype=np.uint8); R = rng.integers(0, 256, (24, 40), dtype=np.uint8)
+    full = oracle.frame_box(L, R, 5, 16)
+    bands = [(0, y, 40, y + 3) for y in range(0, 24, 3)]
+    arrival = [bands[i] for i in rng.permutation(len(bands))]
+    chunks = [(full[y0:y1, x0:x1].ravel(), (x0, y0, x1, y1)) for x0, y0, x1, y1 in arrival]
+    bug = oracle.assemble_disparity_map(chunks, 40, 24, len(bands), faithful_bug=True)
+    x0, y0, x1, y1 = arrival[-1]
+    exp = full.copy(); exp[y0:y1, x0:x1] = 0
+    assert np.array_equal(bug, exp)
+    assert np.array_equal(oracle.assemble_disparity_map(chunks, 40, 24, len(bands), faithful_bug=False), full)
+    assert not oracle.assemble_disparity_map(chunks[:1], 40, 24, 1).any()   # chunks==1 -> all zero
