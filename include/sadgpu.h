@@ -1,0 +1,125 @@
+/*
+ * sadgpu.h — C ABI of libsadgpu.so: the B200 (sm_100a) drop-in for the SAD block-matching
+ * disparity path of conneroisu/steroscopic-hardware, pkg/despair.
+ *
+ * This is the boundary a cgo build of pkg/despair binds (see INTEGRATION.md for the Go
+ * stub).  Plain pointers and sizes only; no C++ types, no exceptions, no torch types.
+ *
+ * What each entry point replaces in the reference:
+ *   sadgpu_compute / sadgpu_submit+sadgpu_wait
+ *       the worker body of SetupConcurrentSAD            pkg/despair/sad.go:47-102
+ *       (per-pixel scan :55-95 and SumAbsoluteDifferences :205-244), for the rows
+ *       [y0,y1) of one left/right *image.Gray pair — i.e. one or many InputChunk regions
+ *       (pkg/despair/sad.go:12-15) of the same frame — and the copy loop of
+ *       AssembleDisparityMap                              pkg/despair/sad.go:186-197
+ *   sadgpu_compute_sharded
+ *       the row-band fan-out of OutputCamera.processDepthMap pkg/camera/output.go:172-190,
+ *       with GPUs in place of goroutines
+ *   block_size / max_disparity arguments
+ *       Parameters{BlockSize, MaxDisparity}               pkg/despair/params.go:34-37
+ *   sadgpu_compute_device
+ *       same computation on device-resident buffers (kernel-only timing, bench.py)
+ *
+ * Semantics are bit-exact with the reference for every pixel:
+ * window side 2*(block_size/2)+1, d = 0..max_disparity inclusive, candidate d skipped when
+ * X-d < 0, windows clamped as in sad.go:212-218, strict '<' argmin in ascending d (lowest d
+ * wins ties), out = uint8(best*255/max_disparity).  Documented deviations: all rows are
+ * written (the dropped-last-chunk bug of sad.go:179-184 is not reproduced); parameters are
+ * read once per call; invalid arguments return an error instead of panicking.
+ *
+ * There is NO CPU fallback: every compute entry point fails with a CUDA error code when no
+ * sm_100 device is usable.
+ */
+#ifndef SADGPU_H
+#define SADGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sadgpu_ctx sadgpu_ctx;
+
+/* Error codes: 0 = OK, negative = argument / state errors, positive = cudaError_t passthrough. */
+#define SADGPU_OK          0
+#define SADGPU_EINVAL    (-1)   /* null pointer, bad size/stride, block_size or max_disparity out of range */
+#define SADGPU_ERANGE    (-2)   /* w/h exceed the context's max_w/max_h, bad stream/device index, bad rows */
+#define SADGPU_ENOMEM    (-3)   /* host allocation failed */
+#define SADGPU_EBUSY     (-4)   /* stream slot already has a frame in flight / bad ticket */
+#define SADGPU_ENODEV    (-5)   /* no usable CUDA device */
+
+/* Supported parameter surface (a superset of the UI range B 3..31, D 16..256,
+ * cmd/handlers/params.go:37,51; the library itself accepts any ints, params.go:21-25). */
+#define SADGPU_MAX_BLOCK_SIZE    31
+#define SADGPU_MAX_DISPARITY     256
+
+/* Optional tuning overrides for tests/benchmarks; 0 = let the planner choose. */
+typedef struct sadgpu_tuning {
+    int rows_per_batch;     /* RB: rows staged through shared memory per iteration */
+    int band_rows;          /* BH: output rows per CTA band                           */
+    int groups_per_chunk;   /* disparity groups (4 disparities each) per CTA chunk     */
+    int kernel_variant;     /* 0 = auto, 1 = generic (shared-memory ring), 2 = register-ring fast path */
+    int reserved[4];
+} sadgpu_tuning;
+
+int  sadgpu_device_count(void);
+
+/* devices == NULL  => devices 0..n_devices-1.  n_streams logical camera streams are created;
+ * stream s lives on devices[s % n_devices] and owns a CUDA stream, pinned upload/download
+ * buffers and device buffers sized for max_w x max_h.  Nothing is allocated per frame. */
+int  sadgpu_create(const int *devices, int n_devices, int max_w, int max_h, int n_streams,
+                   sadgpu_ctx **out);
+void sadgpu_destroy(sadgpu_ctx *ctx);
+
+/* Synchronous: stage -> H2D -> kernel -> D2H -> copy rows [y0,y1) into out (row y lands at
+ * out + (y - y0) * out_stride ... no: see below).  `out` addresses the FULL map: row y is
+ * written at out + y*out_stride, so several calls with disjoint row ranges assemble one
+ * Pix slice exactly like AssembleDisparityMap does.  Full frame: y0 = 0, y1 = h. */
+int  sadgpu_compute(sadgpu_ctx *ctx, int stream,
+                    const uint8_t *left, int left_stride, const uint8_t *right, int right_stride,
+                    int w, int h, int block_size, int max_disparity, int y0, int y1,
+                    uint8_t *out, int out_stride);
+
+/* Asynchronous pair for per-camera pipelining.  submit copies the inputs (no caller pointer is
+ * retained — cgo rule) and enqueues H2D + kernel + D2H on the stream; wait blocks until that
+ * frame is done and copies rows [y0,y1) of the result to `out` (full-map addressing). */
+int  sadgpu_submit(sadgpu_ctx *ctx, int stream,
+                   const uint8_t *left, int left_stride, const uint8_t *right, int right_stride,
+                   int w, int h, int block_size, int max_disparity, int y0, int y1,
+                   uint64_t *ticket);
+int  sadgpu_wait(sadgpu_ctx *ctx, uint64_t ticket, uint8_t *out, int out_stride);
+
+/* One frame split into row bands with a block_size/2 halo over ALL devices of the context
+ * (one band per device, streams 0..n_devices-1), host-side gather into out. */
+int  sadgpu_compute_sharded(sadgpu_ctx *ctx,
+                            const uint8_t *left, int left_stride, const uint8_t *right, int right_stride,
+                            int w, int h, int block_size, int max_disparity,
+                            uint8_t *out, int out_stride);
+
+/* Device-resident: dL/dR/dOut are device pointers on `device` (index into the context's
+ * device list); rows [y0,y1) of dOut are written; enqueued on cuda_stream (a cudaStream_t,
+ * NULL = the legacy default stream) without synchronising.  tuning may be NULL. */
+int  sadgpu_compute_device(sadgpu_ctx *ctx, int device,
+                           const uint8_t *dL, size_t pitch_l, const uint8_t *dR, size_t pitch_r,
+                           int w, int h, int block_size, int max_disparity, int y0, int y1,
+                           uint8_t *dOut, size_t pitch_out, void *cuda_stream,
+                           const sadgpu_tuning *tuning);
+
+/* Pinned host memory from the context's pool: frames that already live here are uploaded
+ * without the staging memcpy (cameras write straight into it). */
+void *sadgpu_host_alloc(sadgpu_ctx *ctx, size_t bytes);
+void  sadgpu_host_free(sadgpu_ctx *ctx, void *p);
+
+/* Introspection used by bench.py / tests. */
+int  sadgpu_last_launch_count(sadgpu_ctx *ctx);    /* kernels launched by the last compute call */
+int  sadgpu_plan_describe(int w, int h, int block_size, int max_disparity, int y0, int y1,
+                          const sadgpu_tuning *tuning, char *buf, size_t buflen);
+const char *sadgpu_strerror(int code);
+const char *sadgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SADGPU_H */

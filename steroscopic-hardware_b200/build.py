@@ -1,0 +1,46 @@
+"""In-tree build of libsadgpu.so (CUDA kernels + C ABI) for sm_100a.
+
+    python steroscopic-hardware_b200/build.py [--force]
+
+nvcc cross-compiles without a GPU.  The .so stays in-tree (git-ignored) so that it travels to
+the GPU box with the snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+ROOT = os.path.dirname(HERE)
+LIB = os.path.join(HERE, "libsadgpu.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def sources():
+    out = [os.path.join(ROOT, "include", "sadgpu.h")]
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp")):
+            out.append(os.path.join(CSRC, f))
+    return out
+
+
+def build_all(force=False, verbose=False):
+    srcs = sources()
+    if force or _stale(LIB, srcs):
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "sadgpu.cu")]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv, verbose=True))

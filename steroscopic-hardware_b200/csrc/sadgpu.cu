@@ -1,0 +1,491 @@
+// sadgpu.cu — C-ABI shim of libsadgpu.so (include/sadgpu.h): context, per-stream pinned and
+// device buffers, the launch planner and the kernel dispatch.  No CPU fallback exists: every
+// compute entry point ends in a kernel launch or an error code.
+#include "../../include/sadgpu.h"
+#include "sad_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+using namespace sadgpu;
+
+namespace {
+
+constexpr int kSmemBudget = 232448;      // 227 KB opt-in dynamic shared memory per CTA on sm_100
+constexpr int kGT = 5;                   // disparity groups per phase-B thread
+constexpr int kMaxThreadsPerColumn = 4;  // K: phase-B threads per pixel column
+constexpr int kMaxDevices = 64;
+
+struct Plan {
+    SadArgs a;
+    dim3 grid;
+    int nthreads;
+    size_t smem;
+    int half;
+    int launches;
+};
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+int validate(int w, int h, int B, int D, int y0, int y1)
+{
+    if (w <= 0 || h <= 0) return SADGPU_EINVAL;
+    if (B < 1 || B > SADGPU_MAX_BLOCK_SIZE || D < 1 || D > SADGPU_MAX_DISPARITY) return SADGPU_EINVAL;
+    if (y0 < 0 || y1 > h || y0 > y1) return SADGPU_ERANGE;
+    return SADGPU_OK;
+}
+
+// Chooses tile geometry.  All quantities are documented in DESIGN.md §3.
+int make_plan(int w, int h, int B, int D, int y0, int y1, const sadgpu_tuning* t, int sm_count, Plan* p)
+{
+    int rc = validate(w, h, B, D, y0, y1);
+    if (rc) return rc;
+    SadArgs& a = p->a;
+    memset(&a, 0, sizeof(a));
+    const int half = B / 2, WIN = 2 * half + 1;
+    p->half = half;
+    a.W = w; a.H = h; a.y0 = y0; a.y1 = y1; a.D = D;
+    a.NG = (D + 4) / 4;                                   // groups of 4 disparities covering 0..D
+    int maxg = kGT * kMaxThreadsPerColumn;
+    if (t && t->groups_per_chunk > 0) maxg = std::min(maxg, t->groups_per_chunk);
+    a.NSTEP = 64;
+    a.TW = a.NSTEP - 2 * half;
+    a.TWp = round_up(a.TW, 32);
+    int RBmax = 0;
+    for (;; --maxg) {
+        if (maxg < 1) return SADGPU_EINVAL;
+        a.NC = ceil_div(a.NG, maxg);
+        a.NGc = ceil_div(a.NG, a.NC);
+        a.K = ceil_div(a.NGc, kGT);
+        a.NGP = a.NGc | 1;                                // odd stride: conflict-free 64-bit column reads
+        a.RW = a.NGc + a.NSTEP / 4;
+        const int ringrow = a.TW * a.NGP * 8;
+        const int perrow = ringrow + a.NSTEP * 4 + a.RW * 4 + a.K * a.TW * 4;
+        const int fixed = WIN * ringrow + round_up(4 * a.NG, 16) + 64;
+        RBmax = (kSmemBudget - fixed) / perrow;
+        if (RBmax >= 4) break;
+    }
+    a.RB = std::min(RBmax, 16);
+    if (t && t->rows_per_batch > 0) a.RB = std::min(RBmax, t->rows_per_batch);
+    a.NR = a.RB + WIN;
+    const int ringrow = a.TW * a.NGP * 8;
+    a.offL = round_up(a.NR * ringrow, 16);
+    a.offR = a.offL + a.RB * a.NSTEP * 4;
+    a.offPk = a.offR + a.RB * a.RW * 4;
+    a.offLut = a.offPk + a.RB * a.K * a.TW * 4;
+    p->smem = (size_t)a.offLut + round_up(4 * a.NG, 16);
+    if (p->smem > (size_t)kSmemBudget) return SADGPU_EINVAL;
+    p->nthreads = 256;
+    if (a.TWp * a.K > p->nthreads) return SADGPU_EINVAL;
+
+    const int rows = y1 - y0;
+    const int nstrips = ceil_div(w, a.TW);
+    int nbands = 1;
+    if (t && t->band_rows > 0) {
+        a.BH = std::min(std::max(1, t->band_rows), std::max(rows, 1));
+        nbands = ceil_div(std::max(rows, 1), a.BH);
+    } else {
+        // minimise waves x rows-per-CTA (one CTA per SM: the H ring fills shared memory)
+        long best_cost = -1;
+        for (int nb = 1; nb <= std::max(1, std::min(rows, 256)); ++nb) {
+            const int bh = ceil_div(std::max(rows, 1), nb);
+            const long ctas = (long)nstrips * nb * a.NC;
+            const long waves = (ctas + sm_count - 1) / sm_count;
+            const long cost = waves * (round_up(bh + 2 * half, a.RB) + 2);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; nbands = nb; }
+        }
+        a.BH = ceil_div(std::max(rows, 1), nbands);
+        nbands = ceil_div(std::max(rows, 1), a.BH);
+    }
+    p->grid = dim3(nstrips, nbands, a.NC);
+    p->launches = a.NC == 1 ? 1 : 3;
+    return SADGPU_OK;
+}
+
+template <int HALF>
+cudaError_t launch_generic(const Plan& p, cudaStream_t s, bool* attr_done)
+{
+    auto k = sad_generic_kernel<HALF, kGT>;
+    if (!*attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+        if (e != cudaSuccess) return e;
+        *attr_done = true;
+    }
+    k<<<p.grid, p.nthreads, p.smem, s>>>(p.a);
+    return cudaGetLastError();
+}
+
+typedef cudaError_t (*launch_fn)(const Plan&, cudaStream_t, bool*);
+const launch_fn kLaunchGeneric[16] = {
+    launch_generic<0>, launch_generic<1>, launch_generic<2>, launch_generic<3>,
+    launch_generic<4>, launch_generic<5>, launch_generic<6>, launch_generic<7>,
+    launch_generic<8>, launch_generic<9>, launch_generic<10>, launch_generic<11>,
+    launch_generic<12>, launch_generic<13>, launch_generic<14>, launch_generic<15>};
+
+struct Slot {
+    int dev_index = 0, device = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    uint8_t *hL = nullptr, *hR = nullptr, *hOut = nullptr;     // pinned staging
+    uint8_t *dL = nullptr, *dR = nullptr, *dOut = nullptr;     // device, pitched
+    uint32_t* gkey = nullptr;
+    size_t pitch = 0;
+    std::mutex mu;
+    bool busy = false;
+    uint64_t seq = 0;
+    int w = 0, h = 0, y0 = 0, y1 = 0;                          // frame in flight
+    bool out_direct = false;
+};
+
+}  // namespace
+
+struct sadgpu_ctx {
+    std::vector<int> devices;
+    std::vector<int> sm_count;
+    std::vector<Slot*> slots;
+    int max_w = 0, max_h = 0;
+    std::atomic<int> last_launches{0};
+    std::mutex pool_mu;
+    std::vector<std::pair<uint8_t*, size_t>> pool;
+    bool attr_done[kMaxDevices][16];
+    std::vector<uint32_t*> dev_gkey;       // per device scratch for sadgpu_compute_device
+    std::mutex dev_mu;
+};
+
+namespace {
+
+bool in_pool(sadgpu_ctx* c, const void* p, size_t bytes)
+{
+    std::lock_guard<std::mutex> g(c->pool_mu);
+    const uint8_t* q = static_cast<const uint8_t*>(p);
+    for (auto& r : c->pool)
+        if (q >= r.first && q + bytes <= r.first + r.second) return true;
+    return false;
+}
+
+// Enqueue fill (if chunked) + kernel + finalize (if chunked) on stream s.  Device must be current.
+int enqueue(sadgpu_ctx* c, int dev_index, const Plan& pl, uint32_t* gkey, cudaStream_t s)
+{
+    Plan p = pl;
+    if (p.a.NC > 1) {
+        if (!gkey) return SADGPU_EINVAL;
+        p.a.gkey = gkey;
+        const size_t n = (size_t)p.a.W * (p.a.y1 - p.a.y0);
+        sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, s>>>(gkey + (size_t)p.a.y0 * p.a.W, n, 0xFFFFFFFFu);
+    }
+    cudaError_t e = kLaunchGeneric[p.half](p, s, &c->attr_done[dev_index][p.half]);
+    if (e != cudaSuccess) return (int)e;
+    if (p.a.NC > 1) {
+        dim3 g(ceil_div(p.a.W, 256), p.a.y1 - p.a.y0);
+        sad_finalize_kernel<<<g, 256, 0, s>>>(gkey, p.a.out, p.a.W, p.a.y0, p.a.y1, p.a.pitchOut, p.a.D);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return (int)e;
+    }
+    c->last_launches.store(p.launches);
+    return SADGPU_OK;
+}
+
+int check_io(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, const uint8_t* r, int rs, int w, int h)
+{
+    if (!c || !l || !r) return SADGPU_EINVAL;
+    if (stream < 0 || stream >= (int)c->slots.size()) return SADGPU_ERANGE;
+    if (w <= 0 || h <= 0 || ls < w || rs < w) return SADGPU_EINVAL;
+    if (w > c->max_w || h > c->max_h) return SADGPU_ERANGE;
+    return SADGPU_OK;
+}
+
+// Stage rows [ys,ye) of a host image and enqueue the H2D copy.  Pinned pool memory is uploaded in place.
+int upload(sadgpu_ctx* c, Slot* s, const uint8_t* src, int stride, uint8_t* pinned, uint8_t* dev, int w, int ys, int ye)
+{
+    const int n = ye - ys;
+    if (n <= 0) return SADGPU_OK;
+    const uint8_t* from = src + (size_t)ys * stride;
+    size_t from_pitch = (size_t)stride;
+    if (!in_pool(c, from, (size_t)(n - 1) * stride + w)) {
+        uint8_t* st = pinned + (size_t)ys * s->pitch;
+        if ((size_t)stride == s->pitch) memcpy(st, from, (size_t)(n - 1) * stride + w);
+        else for (int y = 0; y < n; ++y) memcpy(st + (size_t)y * s->pitch, from + (size_t)y * stride, (size_t)w);
+        from = st; from_pitch = s->pitch;
+    }
+    cudaError_t e = cudaMemcpy2DAsync(dev + (size_t)ys * s->pitch, s->pitch, from, from_pitch, (size_t)w, (size_t)n,
+                                      cudaMemcpyHostToDevice, s->st);
+    return e == cudaSuccess ? SADGPU_OK : (int)e;
+}
+
+int submit_locked(sadgpu_ctx* c, Slot* s, const uint8_t* l, int ls, const uint8_t* r, int rs,
+                  int w, int h, int B, int D, int y0, int y1, uint8_t* direct_out, int direct_stride)
+{
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return (int)e;
+    Plan p;
+    int rc = make_plan(w, h, B, D, y0, y1, nullptr, c->sm_count[s->dev_index], &p);
+    if (rc) return rc;
+    const int half = B / 2;
+    const int ys = std::max(0, y0 - half), ye = std::min(h, y1 + half);
+    if ((rc = upload(c, s, l, ls, s->hL, s->dL, w, ys, ye))) return rc;
+    if ((rc = upload(c, s, r, rs, s->hR, s->dR, w, ys, ye))) return rc;
+    p.a.L = s->dL; p.a.R = s->dR; p.a.out = s->dOut;
+    p.a.pitchL = p.a.pitchR = p.a.pitchOut = (int)s->pitch;
+    if (y1 > y0) {
+        if ((rc = enqueue(c, s->dev_index, p, s->gkey, s->st))) return rc;
+        s->out_direct = direct_out != nullptr;
+        uint8_t* dst = direct_out ? direct_out + (size_t)y0 * direct_stride : s->hOut + (size_t)y0 * s->pitch;
+        const size_t dpitch = direct_out ? (size_t)direct_stride : s->pitch;
+        e = cudaMemcpy2DAsync(dst, dpitch, s->dOut + (size_t)y0 * s->pitch, s->pitch, (size_t)w, (size_t)(y1 - y0),
+                              cudaMemcpyDeviceToHost, s->st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    e = cudaEventRecord(s->done, s->st);
+    if (e != cudaSuccess) return (int)e;
+    s->busy = true; s->w = w; s->h = h; s->y0 = y0; s->y1 = y1;
+    return SADGPU_OK;
+}
+
+int wait_locked(sadgpu_ctx* c, Slot* s, uint8_t* out, int out_stride)
+{
+    (void)c;
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e == cudaSuccess) e = cudaEventSynchronize(s->done);
+    s->busy = false;
+    if (e != cudaSuccess) return (int)e;
+    if (!s->out_direct) {
+        if (!out || out_stride < s->w) return SADGPU_EINVAL;
+        for (int y = s->y0; y < s->y1; ++y)
+            memcpy(out + (size_t)y * out_stride, s->hOut + (size_t)y * s->pitch, (size_t)s->w);
+    }
+    return SADGPU_OK;
+}
+
+void free_slot(Slot* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->st) { cudaStreamSynchronize(s->st); cudaStreamDestroy(s->st); }
+    if (s->done) cudaEventDestroy(s->done);
+    cudaFreeHost(s->hL); cudaFreeHost(s->hR); cudaFreeHost(s->hOut);
+    cudaFree(s->dL); cudaFree(s->dR); cudaFree(s->dOut); cudaFree(s->gkey);
+    delete s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sadgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sadgpu_create(const int* devices, int n_devices, int max_w, int max_h, int n_streams, sadgpu_ctx** out)
+{
+    if (!out || n_devices < 1 || n_devices > kMaxDevices || max_w <= 0 || max_h <= 0 || n_streams < 1)
+        return SADGPU_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) { cudaGetLastError(); return ndev == 0 ? SADGPU_ENODEV : (int)e; }
+    if (ndev == 0) return SADGPU_ENODEV;
+    sadgpu_ctx* c = new (std::nothrow) sadgpu_ctx();
+    if (!c) return SADGPU_ENOMEM;
+    memset(c->attr_done, 0, sizeof(c->attr_done));
+    c->max_w = max_w; c->max_h = max_h;
+    for (int i = 0; i < n_devices; ++i) {
+        const int d = devices ? devices[i] : i;
+        if (d < 0 || d >= ndev) { delete c; return SADGPU_ERANGE; }
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, d)) != cudaSuccess) { delete c; return (int)e; }
+        if (prop.major != 10) { delete c; return SADGPU_ENODEV; }     // sm_100a cubin only, no fallback
+        c->devices.push_back(d);
+        c->sm_count.push_back(prop.multiProcessorCount);
+    }
+    c->dev_gkey.assign(n_devices, nullptr);
+    const size_t pitch = (size_t)round_up(max_w, 256);
+    const size_t img = pitch * (size_t)max_h;
+    for (int i = 0; i < n_streams; ++i) {
+        Slot* s = new (std::nothrow) Slot();
+        if (!s) { sadgpu_destroy(c); return SADGPU_ENOMEM; }
+        c->slots.push_back(s);
+        s->dev_index = i % n_devices; s->device = c->devices[s->dev_index]; s->pitch = pitch;
+        e = cudaSetDevice(s->device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hL, img, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hR, img, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hOut, img, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->dL, img);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->dR, img);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->dOut, img);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->gkey, (size_t)max_w * max_h * sizeof(uint32_t));
+        if (e != cudaSuccess) { sadgpu_destroy(c); return (int)e; }
+    }
+    *out = c;
+    return SADGPU_OK;
+}
+
+void sadgpu_destroy(sadgpu_ctx* c)
+{
+    if (!c) return;
+    for (Slot* s : c->slots) free_slot(s);
+    for (size_t i = 0; i < c->dev_gkey.size(); ++i)
+        if (c->dev_gkey[i]) { cudaSetDevice(c->devices[i]); cudaFree(c->dev_gkey[i]); }
+    for (auto& r : c->pool) cudaFreeHost(r.first);
+    delete c;
+}
+
+int sadgpu_compute(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, const uint8_t* r, int rs,
+                   int w, int h, int B, int D, int y0, int y1, uint8_t* out, int out_stride)
+{
+    int rc = check_io(c, stream, l, ls, r, rs, w, h);
+    if (rc) return rc;
+    if (!out || out_stride < w) return SADGPU_EINVAL;
+    if ((rc = validate(w, h, B, D, y0, y1))) return rc;
+    Slot* s = c->slots[stream];
+    std::lock_guard<std::mutex> g(s->mu);
+    if (s->busy) return SADGPU_EBUSY;
+    uint8_t* direct = nullptr;
+    if (y1 > y0 && in_pool(c, out + (size_t)y0 * out_stride, (size_t)(y1 - y0 - 1) * out_stride + w)) direct = out;
+    rc = submit_locked(c, s, l, ls, r, rs, w, h, B, D, y0, y1, direct, out_stride);
+    if (rc) { cudaStreamSynchronize(s->st); s->busy = false; return rc; }
+    return wait_locked(c, s, out, out_stride);
+}
+
+int sadgpu_submit(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, const uint8_t* r, int rs,
+                  int w, int h, int B, int D, int y0, int y1, uint64_t* ticket)
+{
+    int rc = check_io(c, stream, l, ls, r, rs, w, h);
+    if (rc) return rc;
+    if (!ticket) return SADGPU_EINVAL;
+    if ((rc = validate(w, h, B, D, y0, y1))) return rc;
+    Slot* s = c->slots[stream];
+    std::lock_guard<std::mutex> g(s->mu);
+    if (s->busy) return SADGPU_EBUSY;
+    rc = submit_locked(c, s, l, ls, r, rs, w, h, B, D, y0, y1, nullptr, 0);
+    if (rc) { cudaStreamSynchronize(s->st); s->busy = false; return rc; }
+    s->seq++;
+    *ticket = (s->seq << 16) | (uint64_t)stream;
+    return SADGPU_OK;
+}
+
+int sadgpu_wait(sadgpu_ctx* c, uint64_t ticket, uint8_t* out, int out_stride)
+{
+    if (!c) return SADGPU_EINVAL;
+    const int stream = (int)(ticket & 0xFFFF);
+    if (stream >= (int)c->slots.size()) return SADGPU_EBUSY;
+    Slot* s = c->slots[stream];
+    std::lock_guard<std::mutex> g(s->mu);
+    if (!s->busy || s->seq != (ticket >> 16)) return SADGPU_EBUSY;
+    return wait_locked(c, s, out, out_stride);
+}
+
+int sadgpu_compute_sharded(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_t* r, int rs,
+                           int w, int h, int B, int D, uint8_t* out, int out_stride)
+{
+    if (!c) return SADGPU_EINVAL;
+    const int n = (int)std::min(c->devices.size(), c->slots.size());
+    int rc = check_io(c, 0, l, ls, r, rs, w, h);
+    if (rc) return rc;
+    if (!out || out_stride < w) return SADGPU_EINVAL;
+    if ((rc = validate(w, h, B, D, 0, h))) return rc;
+    std::vector<uint64_t> tk(n, 0);
+    std::vector<int> started(n, 0);
+    int first_err = 0;
+    for (int i = 0; i < n; ++i) {                       // row band i -> device i, halo handled by submit
+        const int y0 = (int)((long)h * i / n), y1 = (int)((long)h * (i + 1) / n);
+        rc = sadgpu_submit(c, i, l, ls, r, rs, w, h, B, D, y0, y1, &tk[i]);
+        if (rc) { first_err = rc; break; }
+        started[i] = 1;
+    }
+    for (int i = 0; i < n; ++i) {                       // host-side gather: disjoint rows of one Pix
+        if (!started[i]) continue;
+        rc = sadgpu_wait(c, tk[i], out, out_stride);
+        if (rc && !first_err) first_err = rc;
+    }
+    return first_err;
+}
+
+int sadgpu_compute_device(sadgpu_ctx* c, int device, const uint8_t* dL, size_t pitch_l, const uint8_t* dR, size_t pitch_r,
+                          int w, int h, int B, int D, int y0, int y1, uint8_t* dOut, size_t pitch_out,
+                          void* cuda_stream, const sadgpu_tuning* tuning)
+{
+    if (!c || !dL || !dR || !dOut) return SADGPU_EINVAL;
+    if (device < 0 || device >= (int)c->devices.size()) return SADGPU_ERANGE;
+    if (pitch_l < (size_t)w || pitch_r < (size_t)w || pitch_out < (size_t)w) return SADGPU_EINVAL;
+    Plan p;
+    int rc = make_plan(w, h, B, D, y0, y1, tuning, c->sm_count[device], &p);
+    if (rc) return rc;
+    if (y1 == y0) return SADGPU_OK;
+    cudaError_t e = cudaSetDevice(c->devices[device]);
+    if (e != cudaSuccess) return (int)e;
+    uint32_t* gkey = nullptr;
+    if (p.a.NC > 1) {
+        if (w > c->max_w || h > c->max_h) return SADGPU_ERANGE;
+        std::lock_guard<std::mutex> g(c->dev_mu);
+        if (!c->dev_gkey[device]) {
+            e = cudaMalloc((void**)&c->dev_gkey[device], (size_t)c->max_w * c->max_h * sizeof(uint32_t));
+            if (e != cudaSuccess) return (int)e;
+        }
+        gkey = c->dev_gkey[device];
+    }
+    p.a.L = dL; p.a.R = dR; p.a.out = dOut;
+    p.a.pitchL = (int)pitch_l; p.a.pitchR = (int)pitch_r; p.a.pitchOut = (int)pitch_out;
+    return enqueue(c, device, p, gkey, (cudaStream_t)cuda_stream);
+}
+
+void* sadgpu_host_alloc(sadgpu_ctx* c, size_t bytes)
+{
+    if (!c || bytes == 0) return nullptr;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> g(c->pool_mu);
+    c->pool.emplace_back(static_cast<uint8_t*>(p), bytes);
+    return p;
+}
+
+void sadgpu_host_free(sadgpu_ctx* c, void* p)
+{
+    if (!c || !p) return;
+    std::lock_guard<std::mutex> g(c->pool_mu);
+    for (size_t i = 0; i < c->pool.size(); ++i)
+        if (c->pool[i].first == p) { cudaFreeHost(p); c->pool.erase(c->pool.begin() + i); return; }
+}
+
+int sadgpu_last_launch_count(sadgpu_ctx* c) { return c ? c->last_launches.load() : 0; }
+
+int sadgpu_plan_describe(int w, int h, int B, int D, int y0, int y1, const sadgpu_tuning* t, char* buf, size_t buflen)
+{
+    Plan p;
+    int rc = make_plan(w, h, B, D, y0, y1, t, 148, &p);
+    if (rc) return rc;
+    if (buf && buflen)
+        snprintf(buf, buflen,
+                 "{\"variant\":\"generic\",\"half\":%d,\"NG\":%d,\"NC\":%d,\"NGc\":%d,\"K\":%d,\"TW\":%d,\"NSTEP\":%d,"
+                 "\"RB\":%d,\"NR\":%d,\"BH\":%d,\"grid\":[%u,%u,%u],\"threads\":%d,\"smem\":%zu,\"launches\":%d}",
+                 p.half, p.a.NG, p.a.NC, p.a.NGc, p.a.K, p.a.TW, p.a.NSTEP, p.a.RB, p.a.NR, p.a.BH,
+                 p.grid.x, p.grid.y, p.grid.z, p.nthreads, p.smem, p.launches);
+    return SADGPU_OK;
+}
+
+const char* sadgpu_strerror(int code)
+{
+    switch (code) {
+        case SADGPU_OK: return "ok";
+        case SADGPU_EINVAL: return "invalid argument (null pointer, stride < width, block_size not in 1..31 or max_disparity not in 1..256)";
+        case SADGPU_ERANGE: return "argument out of range (image larger than the context, bad stream/device index or row range)";
+        case SADGPU_ENOMEM: return "host allocation failed";
+        case SADGPU_EBUSY: return "stream slot busy or stale ticket";
+        case SADGPU_ENODEV: return "no usable sm_100 CUDA device (there is no CPU fallback)";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown sadgpu error";
+    }
+}
+
+const char* sadgpu_version(void) { return "sadgpu 0.1 (sm_100a)"; }
+
+}  // extern "C"

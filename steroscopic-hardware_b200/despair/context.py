@@ -1,0 +1,115 @@
+"""Thin object wrapper over the C ABI (one sadgpu_ctx).  numpy in / numpy out for the host
+entry points, raw device pointers (e.g. torch.Tensor.data_ptr()) for the device-resident one."""
+import ctypes
+import json
+
+import numpy as np
+
+from . import _native as N
+
+
+def _u8_2d(a, name):
+    a = np.asarray(a)
+    if a.dtype != np.uint8 or a.ndim != 2:
+        raise ValueError(f"{name}: expected a 2-D uint8 array (an image.Gray Pix plane)")
+    if a.strides[1] != 1:
+        a = np.ascontiguousarray(a)
+    return a
+
+
+class Context:
+    def __init__(self, devices=None, max_w=1920, max_h=1080, n_streams=1):
+        L = N.lib()
+        if devices is None:
+            devices = [0]
+        arr = (ctypes.c_int * len(devices))(*devices)
+        h = ctypes.c_void_p()
+        N.check(L.sadgpu_create(arr, len(devices), max_w, max_h, n_streams, ctypes.byref(h)))
+        self._h = h
+        self._L = L
+        self.devices = list(devices)
+        self.n_streams = n_streams
+        self.max_w, self.max_h = max_w, max_h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.sadgpu_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- host entry points -------------------------------------------------------------
+    def compute(self, left, right, block_size, max_disparity, y0=0, y1=None, stream=0, out=None):
+        l = _u8_2d(left, "left"); r = _u8_2d(right, "right")
+        if l.shape != r.shape:
+            raise N.SadGpuError(N.lib().sadgpu_compute.__self__ and -1)
+        h, w = l.shape
+        y1 = h if y1 is None else y1
+        if out is None:
+            out = np.zeros((h, w), np.uint8)
+        N.check(self._L.sadgpu_compute(self._h, stream, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
+                                        w, h, block_size, max_disparity, y0, y1, out.ctypes.data, out.strides[0]))
+        return out
+
+    def submit(self, left, right, block_size, max_disparity, y0=0, y1=None, stream=0):
+        l = _u8_2d(left, "left"); r = _u8_2d(right, "right")
+        h, w = l.shape
+        y1 = h if y1 is None else y1
+        t = ctypes.c_uint64()
+        N.check(self._L.sadgpu_submit(self._h, stream, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
+                                       w, h, block_size, max_disparity, y0, y1, ctypes.byref(t)))
+        return t.value
+
+    def wait(self, ticket, out):
+        N.check(self._L.sadgpu_wait(self._h, ticket, out.ctypes.data, out.strides[0]))
+        return out
+
+    def compute_sharded(self, left, right, block_size, max_disparity, out=None):
+        l = _u8_2d(left, "left"); r = _u8_2d(right, "right")
+        h, w = l.shape
+        if out is None:
+            out = np.zeros((h, w), np.uint8)
+        N.check(self._L.sadgpu_compute_sharded(self._h, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
+                                                w, h, block_size, max_disparity, out.ctypes.data, out.strides[0]))
+        return out
+
+    # -- device-resident entry point -----------------------------------------------------
+    def compute_device(self, dL, pitch_l, dR, pitch_r, w, h, block_size, max_disparity, dOut, pitch_out,
+                       y0=0, y1=None, device=0, cuda_stream=0, tuning=None):
+        y1 = h if y1 is None else y1
+        tp = None
+        if tuning:
+            t = N.Tuning(); [setattr(t, k, v) for k, v in tuning.items()]
+            tp = ctypes.byref(t)
+        N.check(self._L.sadgpu_compute_device(self._h, device, dL, pitch_l, dR, pitch_r, w, h, block_size,
+                                               max_disparity, y0, y1, dOut, pitch_out, cuda_stream, tp))
+
+    # -- pinned pool -----------------------------------------------------------------------
+    def host_array(self, shape):
+        n = int(np.prod(shape))
+        p = self._L.sadgpu_host_alloc(self._h, n)
+        if not p:
+            raise MemoryError("sadgpu_host_alloc failed")
+        buf = (ctypes.c_uint8 * n).from_address(p)
+        a = np.frombuffer(buf, np.uint8).reshape(shape)
+        return a
+
+    def last_launch_count(self):
+        return self._L.sadgpu_last_launch_count(self._h)
+
+
+def plan_describe(w, h, block_size, max_disparity, y0=0, y1=None, tuning=None):
+    y1 = h if y1 is None else y1
+    buf = ctypes.create_string_buffer(1024)
+    tp = None
+    if tuning:
+        t = N.Tuning(); [setattr(t, k, v) for k, v in tuning.items()]
+        tp = ctypes.byref(t)
+    N.check(N.lib().sadgpu_plan_describe(w, h, block_size, max_disparity, y0, y1, tp, buf, 1024))
+    return json.loads(buf.value.decode())
