@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the SAD block-matching disparity path on B200.
+
+Workload (BASELINE.json metric, configs[2] / SURVEY.md §8(d) cfg3): synthetic 1920x1080 grayscale
+stereo stream, block 9, max disparity 128.  One *step* = one pass of the hot path over a batch of
+FRAMES frame pairs per GPU (inputs 2*FRAMES*W*H bytes > the 126 MB L2, so every step streams from
+HBM).  Frame-sharded over ranks, no collective on the data path: weak scaling.
+
+  value        whole-job Mpix*D/s, inputs resident in HBM, CUDA events on the launch stream
+  e2e          same metric through the C ABI (sadgpu_submit / sadgpu_wait) with host buffers:
+               pinned H2D of both images and D2H of the map inside the timed region
+  roofline     integer-ALU roofline (the binding one): 6 int-ops per evaluation
+               against the measured 64 lane-ops/clk/SM; HBM figures beside it
+  cpu_baseline the oracle's literal restatement of pkg/despair on the host cores (rank 0, N=1)
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "steroscopic-hardware_b200"))
+
+import numpy as np
+
+W, H, B, D = 1920, 1080, 9, 128
+FRAMES = 64                       # frame pairs per step per GPU: 265 MB of input > L2
+OPS_PER_EVAL = 6                  # 1 abs-diff + 2 + 2 running-sum add/sub + 1 compare-select
+METRIC = "disparity_evals_per_sec_1080p_D128_B9"
+UNIT = "Mpix*D/s"
+
+
+def stream_frame(seed, h=H, w=W, ramp=56):
+    """cfg3 generator, SURVEY.md §8(d): textured frame, disparity ramp 8..8+ramp, +-2 noise on R."""
+    rng = np.random.default_rng(seed)
+    T = rng.integers(0, 256, (h, w + 128 + 8 + ramp + 2), dtype=np.uint8).astype(np.uint16)
+    T = ((T[:, :-2] + T[:, 1:-1] + T[:, 2:]) // 3).astype(np.uint8)
+    delta = 8 + (ramp * np.arange(h)) // h
+    L = np.ascontiguousarray(T[:, 128:128 + w])
+    R = np.take_along_axis(T, np.arange(w)[None, :] + 128 + delta[:, None], axis=1)
+    R = np.clip(R.astype(np.int16) + rng.integers(-2, 3, R.shape), 0, 255).astype(np.uint8)
+    return L, R
+
+
+def mpixd(frames, seconds):
+    return W * H * D * frames / seconds / 1e6
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(frames_rows, threads, steps, warmup):
+    """Times the oracle's literal restatement of pkg/despair (row bands of H/128 rows pulled by a
+    thread pool, exactly the production chunking) on a bounded sample: `frames_rows` rows of one
+    cfg3 frame per step."""
+    from oracle import oracle as O
+    O.build()
+    L, R = stream_frame(1234)
+    y0 = (H - frames_rows) // 2
+    for _ in range(warmup):
+        O.frame_literal_mt(L, R, B, D, threads=threads, y0=y0, y1=y0 + max(8, frames_rows // 8))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = O.frame_literal_mt(L, R, B, D, threads=threads, y0=y0, y1=y0 + frames_rows)
+    dt = time.perf_counter() - t0
+    frames = steps * frames_rows / H
+    return mpixd(frames, dt), dt / steps, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
+    workload = {"workload": "cfg3 synthetic 1920x1080 stereo stream, block 9, max disparity 128",
+                "frames_per_step_per_gpu": args.frames, "sharding": "frames across ranks, no collective",
+                "l2_policy": "inputs larger than L2 (2*frames*W*H bytes streamed per step)"}
+
+    if args.impl == "reference":
+        # The reference's own CPU implementation of the path (oracle port: Go toolchain absent), all host threads.
+        if rank != 0:
+            return
+        rows = 270                                     # bounded sample: a quarter frame per step
+        v, sec, _ = cpu_reference_run(rows, cores, max(1, args.steps), min(args.warmup, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{rows} rows of one cfg3 frame per step, literal O(B^2 D) algorithm, "
+                                           f"row bands of H/128 rows on {cores} pthreads"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import despair
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the SAD path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_streams = 4
+    ctx = despair.Context([local_rank], W, H, n_streams)
+
+    # ---- synthetic inputs: 8 distinct generated frames tiled to FRAMES (generation is slow on the host) ----
+    nuniq = 8
+    gen = [stream_frame(1234 + rank * 1024 + k) for k in range(nuniq)]
+    F = args.frames
+    dL = torch.empty((F, H, W), dtype=torch.uint8, device="cuda")
+    dR = torch.empty((F, H, W), dtype=torch.uint8, device="cuda")
+    for k in range(F):
+        dL[k].copy_(torch.from_numpy(gen[k % nuniq][0])); dR[k].copy_(torch.from_numpy(gen[k % nuniq][1]))
+    dO = torch.zeros((F, H, W), dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream()
+    st = stream.cuda_stream
+
+    def step_device():
+        for k in range(F):
+            ctx.compute_device(dL[k].data_ptr(), W, dR[k].data_ptr(), W, W, H, B, D, dO[k].data_ptr(), W, cuda_stream=st)
+
+    launches_per_frame = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    launches_per_frame = ctx.last_launch_count()
+    barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = mpixd(args.steps * F * world, ms_max * 1e-3)
+
+    # ---- parity of the timed work (one frame vs oracle rows) ----
+    parity = None
+    if rank == 0:
+        from oracle import oracle as O
+        O.build()
+        exp = O.frame_box(gen[0][0], gen[0][1], B, D, 520, 536)
+        parity = bool(np.array_equal(dO[0].cpu().numpy()[520:536], exp))
+
+    # ---- e2e: C ABI with host buffers (pinned pool), submit/wait pipelined over n_streams ----
+    pin = [(ctx.host_array((H, W)), ctx.host_array((H, W))) for _ in range(nuniq)]
+    for k in range(nuniq):
+        pin[k][0][:] = gen[k][0]; pin[k][1][:] = gen[k][1]
+    outs = [ctx.host_array((H, W)) for _ in range(n_streams)]
+
+    def step_e2e():
+        tickets = [None] * n_streams
+        for k in range(F):
+            s = k % n_streams
+            if tickets[s] is not None:
+                ctx.wait(tickets[s], outs[s])
+            tickets[s] = ctx.submit(pin[k % nuniq][0], pin[k % nuniq][1], B, D, stream=s)
+        for s in range(n_streams):
+            if tickets[s] is not None:
+                ctx.wait(tickets[s], outs[s])
+
+    e2e_steps = max(1, min(args.steps, 5))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = mpixd(e2e_steps * F * world, float(t.item()))
+    e2e_parity = None
+    if rank == 0:
+        e2e_parity = bool(np.array_equal(outs[(F - 1) % n_streams][520:536],
+                                         O.frame_box(gen[(F - 1) % nuniq][0], gen[(F - 1) % nuniq][1], B, D, 520, 536)))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (per launch == per frame), integer ALU ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    try:
+        ip = json.load(open(os.path.join(ROOT, "profiles", "r01_int_peaks.json")))
+        p_int = ip["iadd3"]["lane_ops_per_clk_per_sm"] * ip["sms"] * ip["clock_rate_khz"] * 1e3 / 1e12
+        p_src = "profiles/r01_int_peaks.json: measured 63.9 IADD3 lane-ops/clk/SM x 148 SMs x 1.965 GHz"
+    except Exception:
+        p_int, p_src = 148 * 64 * 1.965e9 / 1e12, "theoretical 148 SM x 64 lanes x 1.965 GHz"
+    us_per_frame = ms_max * 1e3 / (args.steps * F)
+    evals = W * H * (D + 1)
+    achieved = OPS_PER_EVAL * evals / (us_per_frame * 1e-6) / 1e12
+    alg_bytes = 3 * W * H
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "int_alu", "achieved": achieved, "peak": p_int, "unit": "Tiop/s", "frac": achieved / p_int,
+                "traffic": traffic, "ops_per_eval": OPS_PER_EVAL, "evals_per_launch": evals,
+                "kernel_us_per_launch": us_per_frame, "peak_source": p_src,
+                "hbm": {"achieved": alg_bytes / (us_per_frame * 1e-6) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (us_per_frame * 1e-6) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"}}
+
+    cpu_baseline = None
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        rows = 540                                     # half a frame: ~10-30 core-seconds of literal SAD
+        v, sec, out = cpu_reference_run(rows, cores, 1, 0)
+        ok = bool(np.array_equal(out, ctx.compute(*stream_frame(1234), B, D)[(H - rows) // 2:(H - rows) // 2 + rows]))
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{rows} rows of one cfg3 frame ({sec:.2f} s), literal pkg/despair algorithm "
+                                  f"(oracle, Go toolchain unavailable), H/128-row bands on {cores} pthreads",
+                        "matches_gpu": ok}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload,
+            "frames_per_sec": args.steps * F * world / (ms_max * 1e-3), "us_per_frame_per_gpu": us_per_frame,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * F, "d2h_bytes_per_step": W * H * F,
+                    "frames_per_sec": e2e_steps * F * world / float(t.item()), "parity": e2e_parity,
+                    "how": f"sadgpu_submit/sadgpu_wait, pinned host buffers, {n_streams} streams in flight"},
+            "gpu_launches": args.steps * F * launches_per_frame, "launches_per_frame": launches_per_frame,
+            "parity": parity, "plan": despair.plan_describe(W, H, B, D), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

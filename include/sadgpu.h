@@ -73,10 +73,10 @@ int  sadgpu_create(const int *devices, int n_devices, int max_w, int max_h, int 
                    sadgpu_ctx **out);
 void sadgpu_destroy(sadgpu_ctx *ctx);
 
-/* Synchronous: stage -> H2D -> kernel -> D2H -> copy rows [y0,y1) into out (row y lands at
- * out + (y - y0) * out_stride ... no: see below).  `out` addresses the FULL map: row y is
- * written at out + y*out_stride, so several calls with disjoint row ranges assemble one
- * Pix slice exactly like AssembleDisparityMap does.  Full frame: y0 = 0, y1 = h. */
+/* Synchronous: stage -> H2D -> kernel -> D2H -> copy rows [y0,y1) into out.  `out` addresses
+ * the FULL map: row y is written at out + y*out_stride, so several calls with disjoint row
+ * ranges assemble one Pix slice exactly like AssembleDisparityMap does (sad.go:186-197).
+ * Full frame: y0 = 0, y1 = h.  Only rows [y0-h, y1+h) of left/right are read. */
 int  sadgpu_compute(sadgpu_ctx *ctx, int stream,
                     const uint8_t *left, int left_stride, const uint8_t *right, int right_stride,
                     int w, int h, int block_size, int max_disparity, int y0, int y1,

@@ -48,7 +48,7 @@ class Context:
     def compute(self, left, right, block_size, max_disparity, y0=0, y1=None, stream=0, out=None):
         l = _u8_2d(left, "left"); r = _u8_2d(right, "right")
         if l.shape != r.shape:
-            raise N.SadGpuError(N.lib().sadgpu_compute.__self__ and -1)
+            raise N.SadGpuError(-1)     # left.Rect != right.Rect is rejected (SURVEY.md §8 deviations)
         h, w = l.shape
         y1 = h if y1 is None else y1
         if out is None:

@@ -1,0 +1,77 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/sadgpu.h
+declares, plans launches, and fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def native():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sadgpu_build", os.path.join(ROOT, "steroscopic-hardware_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    b.build_all()
+    from despair import _native
+    return _native
+
+
+def test_header_symbols_all_exported(native):
+    hdr = open(os.path.join(ROOT, "include", "sadgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(sadgpu_[a-z_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    L = ctypes.CDLL(native.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(L, s)]
+    assert not missing, missing
+    assert declared == set(native.EXPORTS), (declared ^ set(native.EXPORTS))
+
+
+def test_version_and_strerror(native):
+    L = native.lib()
+    assert b"sm_100a" in L.sadgpu_version()
+    assert b"invalid" in L.sadgpu_strerror(-1)
+    assert b"no CPU fallback" in L.sadgpu_strerror(-5)
+
+
+def test_plans_cover_the_parameter_surface(native):
+    import despair
+    for B in range(1, 32):
+        for D in (1, 16, 64, 128, 255, 256):
+            p = despair.plan_describe(1920, 1080, B, D)
+            assert p["half"] == B // 2 and p["smem"] <= 232448 and p["NC"] * p["NGc"] >= p["NG"]
+            assert p["TW"] == p["NSTEP"] - 2 * (B // 2)
+    p = despair.plan_describe(1920, 1080, 9, 128)
+    assert p["grid"][0] * p["TW"] >= 1920
+
+
+def test_plan_rejects_bad_parameters(native):
+    import despair
+    for (w, h, B, D, y0, y1) in [(0, 10, 9, 64, 0, 10), (10, 10, 0, 64, 0, 10), (10, 10, 32, 64, 0, 10),
+                                 (10, 10, 9, 0, 0, 10), (10, 10, 9, 257, 0, 10)]:
+        with pytest.raises(despair.SadGpuError) as e:
+            despair.plan_describe(w, h, B, D, y0, y1)
+        assert e.value.code == -1
+    with pytest.raises(despair.SadGpuError) as e:
+        despair.plan_describe(10, 10, 9, 64, 5, 11)
+    assert e.value.code == -2
+
+
+def test_no_cpu_fallback_without_gpu(native):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import despair
+    assert native.lib().sadgpu_device_count() == 0
+    with pytest.raises(despair.SadGpuError):
+        despair.Context([0], 64, 64, 1)
+
+
+def test_missing_library_fails_loudly(native, monkeypatch):
+    monkeypatch.setattr(native, "_lib", None)
+    monkeypatch.setattr(native, "LIB_PATH", "/nonexistent/libsadgpu.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        native.lib()

@@ -1,0 +1,220 @@
+"""GPU parity tests proper: libsadgpu.so (through its C ABI) against the oracle and the golden
+fixtures.  Bit-exact: this is integer/byte work."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_gray, GOLDEN
+
+pytestmark = pytest.mark.gpu
+sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import despair
+    c = despair.Context([0], 3840, 2160, 4)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def dev_run(torch, ctx, L, R, B, D, tuning=None, y0=0, y1=None, pitch_pad=0):
+    h, w = L.shape
+    pl = w + pitch_pad
+    dL = torch.zeros((h, pl), dtype=torch.uint8, device="cuda"); dL[:, :w] = torch.from_numpy(L).cuda()
+    dR = torch.zeros((h, pl), dtype=torch.uint8, device="cuda"); dR[:, :w] = torch.from_numpy(R).cuda()
+    dO = torch.full((h, pl), 77, dtype=torch.uint8, device="cuda")
+    ctx.compute_device(dL.data_ptr(), pl, dR.data_ptr(), pl, w, h, B, D, dO.data_ptr(), pl, y0=y0, y1=y1,
+                       cuda_stream=torch.cuda.current_stream().cuda_stream, tuning=tuning)
+    torch.cuda.synchronize()
+    return dO.cpu().numpy()[:, :w]
+
+
+def synth_pair(rng, H, W, kind):
+    if kind == 0:
+        return rng.integers(0, 256, (H, W), dtype=np.uint8), rng.integers(0, 256, (H, W), dtype=np.uint8)
+    if kind == 1:   # shifted texture: a true disparity exists
+        base = rng.integers(0, 256, (H, W + 64), dtype=np.uint8); s = int(rng.integers(0, 40))
+        return base[:, 64:64 + W].copy(), np.roll(base, -s, 1)[:, 64:64 + W].copy()
+    if kind == 2:   # three grey levels: massive ties
+        return rng.integers(0, 3, (H, W), dtype=np.uint8), rng.integers(0, 3, (H, W), dtype=np.uint8)
+    if kind == 3:   # maximum SAD everywhere (255 vs 0): exercises the 16-bit headroom and the poison ordering
+        return np.full((H, W), 255, np.uint8), np.zeros((H, W), np.uint8)
+    return np.full((H, W), 31, np.uint8), np.full((H, W), 31, np.uint8)   # flat: all candidates tie
+
+
+@pytest.mark.parametrize("B", list(range(1, 32)))
+def test_every_block_size_random(torch_mod, ctx, oracle, B):
+    rng = np.random.default_rng(100 + B)
+    for i, D in enumerate((16, 64, 100, 256)):
+        W = int(rng.integers(40, 220)); H = int(rng.integers(20, 80))
+        L, R = synth_pair(rng, H, W, i % 5)
+        assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D), oracle.frame_box(L, R, B, D)), (W, H, B, D)
+
+
+@pytest.mark.parametrize("D", [1, 2, 3, 4, 5, 15, 16, 17, 32, 48, 64, 127, 128, 129, 255, 256])
+def test_every_disparity_grid_point(torch_mod, ctx, oracle, D):
+    rng = np.random.default_rng(200 + D)
+    for i, B in enumerate((3, 9, 16, 31)):
+        W = int(rng.integers(30, 300)); H = int(rng.integers(10, 60))
+        L, R = synth_pair(rng, H, W, (i + D) % 5)
+        assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D), oracle.frame_box(L, R, B, D)), (W, H, B, D)
+
+
+def test_degenerate_shapes(torch_mod, ctx, oracle):
+    rng = np.random.default_rng(5)
+    for (W, H, B, D) in [(1, 1, 1, 1), (1, 1, 31, 256), (2, 50, 9, 64), (50, 2, 9, 64), (5, 5, 31, 256),
+                         (7, 40, 15, 16), (300, 3, 3, 256), (64, 64, 9, 200), (57, 33, 8, 20), (113, 17, 30, 77)]:
+        for kind in (0, 3, 4):
+            L, R = synth_pair(rng, H, W, kind)
+            assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D), oracle.frame_box(L, R, B, D)), (W, H, B, D, kind)
+
+
+def test_tilings_do_not_change_pixels(torch_mod, ctx, oracle):
+    """Forced small batches / bands / disparity chunks: every CTA boundary is crossed."""
+    rng = np.random.default_rng(6)
+    for i in range(40):
+        W = int(rng.integers(20, 260)); H = int(rng.integers(10, 120))
+        B = int(rng.integers(1, 32)); D = int(rng.choice([5, 16, 64, 128, 256]))
+        L, R = synth_pair(rng, H, W, i % 5)
+        tun = dict(rows_per_batch=int(rng.integers(1, 12)), band_rows=int(rng.integers(1, 50)),
+                   groups_per_chunk=int(rng.integers(1, 21)))
+        assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, tun), oracle.frame_box(L, R, B, D)), (W, H, B, D, tun)
+
+
+def test_row_ranges_pitch_and_untouched_rows(torch_mod, ctx, oracle):
+    rng = np.random.default_rng(7)
+    L, R = synth_pair(rng, 90, 200, 1)
+    exp = oracle.frame_box(L, R, 11, 64)
+    got = dev_run(torch_mod, ctx, L, R, 11, 64, y0=17, y1=61, pitch_pad=24)
+    assert np.array_equal(got[17:61], exp[17:61])
+    assert (got[:17] == 77).all() and (got[61:] == 77).all()      # rows outside [y0,y1) are not written
+
+
+def test_golden_cfg1_pairs_host_api(ctx, manifest):
+    for tag, rec in manifest["pairs"].items():
+        L = load_gray(f"L_{tag}_gray.png"); R = load_gray(f"R_{tag}_gray.png")
+        got = ctx.compute(L, R, 9, 64)
+        assert sha(got) == rec["b9_d64_sha256"] == manifest["survey_pins"][f"{tag}_b9_d64"]
+        assert np.array_equal(got, load_gray(f"disp_{tag}_b9_d64.png"))
+    L = load_gray("L_00001_gray.png"); R = load_gray("R_00001_gray.png")
+    assert sha(ctx.compute(L, R, 16, 64)) == manifest["survey_pins"]["00001_b16_d64"]    # init default B=16 (params.go:13-18)
+
+
+def test_golden_cfg2_native_resolution(ctx, manifest):
+    L = load_gray("im0_intended_gray.png"); R = load_gray("im1_intended_gray.png")
+    got = ctx.compute(L, R, 15, 256)
+    assert sha(got) == manifest["survey_pins"]["im0_im1_intended_b15_d256"]
+    z = np.zeros((1080, 1920), np.uint8)         # what LoadPNG as written feeds the path (gray.go:35-37)
+    assert sha(ctx.compute(z, z, 15, 256)) == manifest["survey_pins"]["zeros_1920x1080"]
+
+
+def test_fpga_known_answers_interior(ctx):
+    v = np.load(os.path.join(GOLDEN, "fpga_vectors.npz"))
+    for k in range(4):
+        got = ctx.compute(v["L"][k], v["R"][k], 15, 64)
+        exp = (v["exp_disp_p"][k].astype(int) * 255 // 64).astype(np.uint8)
+        assert np.array_equal(got[:, 71:121], exp[:, 71:121])
+    for k in range(v["hw_sad_L"].shape[0]):       # reference C generator run on random patches
+        got = ctx.compute(v["hw_sad_L"][k], v["hw_sad_R"][k], 15, 64)
+        exp = (v["hw_sad_out"][k].astype(int) * 255 // 64).astype(np.uint8)
+        assert np.array_equal(got[7:121, 71:121], exp[7:121, 71:121])
+
+
+def _stream_frame(seed, H=1080, W=1920, ramp=56):
+    """cfg3/cfg4 generator of SURVEY.md §8(d)."""
+    rng = np.random.default_rng(seed)
+    T = rng.integers(0, 256, (H, W + 128 + 8 + ramp + 2), dtype=np.uint8).astype(np.uint16)
+    T = ((T[:, :-2] + T[:, 1:-1] + T[:, 2:]) // 3).astype(np.uint8)     # light blur for texture
+    delta = 8 + (ramp * np.arange(H)) // H
+    L = T[:, 128:128 + W]
+    idx = (np.arange(W)[None, :] + 128 + delta[:, None])
+    R = np.take_along_axis(T, idx, axis=1)
+    R = np.clip(R.astype(np.int16) + rng.integers(-2, 3, R.shape), 0, 255).astype(np.uint8)
+    return np.ascontiguousarray(L), R
+
+
+def test_cfg3_full_frame_1080p(ctx, oracle):
+    L, R = _stream_frame(1234)
+    got = ctx.compute(L, R, 9, 128)
+    assert np.array_equal(got, oracle.frame_box(L, R, 9, 128))
+    # the planted disparity ramp is recovered in the interior
+    d = (got.astype(int) * 128 + 254) // 255
+    assert abs(int(np.median(d[540, 300:1800])) - (8 + 56 * 540 // 1080)) <= 1
+
+
+def test_cfg4_4k_b31_d256_rows_and_properties(ctx, oracle):
+    L, R = _stream_frame(4321, 2160, 3840, 240)
+    got = ctx.compute(L, R, 31, 256)
+    for (a, b) in [(0, 24), (1000, 1016), (2140, 2160)]:
+        assert np.array_equal(got[a:b], oracle.frame_box(L, R, 31, 256, a, b)), (a, b)
+    assert not got[:, :15].any()                                           # X < h -> 0 (sad.go:212-218)
+    x = np.arange(3840)
+    assert (got.astype(int) <= (np.clip(x - 15, 0, 256) * 255) // 256).all()   # d <= X - h
+    # row-range calls assemble the same map (chunk geometry never changes pixels)
+    out = np.zeros_like(got)
+    for i in range(8):
+        ctx.compute(L, R, 31, 256, y0=270 * i, y1=270 * (i + 1), out=out, stream=i % 4)
+    assert np.array_equal(out, got)
+    # vertical-shift equivariance away from the borders
+    got2 = ctx.compute(L[40:], R[40:], 31, 256)
+    assert np.array_equal(got2[15:-15], got[55:-15])
+
+
+def test_submit_wait_pipelining_and_sharded(ctx, oracle):
+    rng = np.random.default_rng(9)
+    frames = [synth_pair(rng, 120, 320, 1) for _ in range(8)]
+    exp = [oracle.frame_box(L, R, 9, 64) for L, R in frames]
+    outs = [np.zeros((120, 320), np.uint8) for _ in frames]
+    tickets = {}
+    for k, (L, R) in enumerate(frames):
+        s = k % 4
+        if s in tickets:
+            kk, t = tickets.pop(s); ctx.wait(t, outs[kk])
+        tickets[s] = (k, ctx.submit(L, R, 9, 64, stream=s))
+    for s, (kk, t) in tickets.items():
+        ctx.wait(t, outs[kk])
+    for o, e in zip(outs, exp):
+        assert np.array_equal(o, e)
+    assert np.array_equal(ctx.compute_sharded(frames[0][0], frames[0][1], 9, 64), exp[0])
+
+
+def test_pinned_pool_zero_copy_path(ctx, oracle):
+    rng = np.random.default_rng(10)
+    L, R = synth_pair(rng, 100, 256, 1)
+    pL = ctx.host_array((100, 256)); pR = ctx.host_array((100, 256)); pO = ctx.host_array((100, 256))
+    pL[:] = L; pR[:] = R; pO[:] = 0
+    ctx.compute(pL, pR, 7, 32, out=pO)
+    assert np.array_equal(pO, oracle.frame_box(L, R, 7, 32))
+
+
+def test_error_codes(ctx):
+    import despair
+    L = np.zeros((10, 10), np.uint8)
+    for kw, code in [(dict(block_size=0, max_disparity=64), -1), (dict(block_size=33, max_disparity=64), -1),
+                     (dict(block_size=9, max_disparity=0), -1), (dict(block_size=9, max_disparity=300), -1)]:
+        with pytest.raises(despair.SadGpuError) as e:
+            ctx.compute(L, L, **kw)
+        assert e.value.code == code
+    with pytest.raises(despair.SadGpuError) as e:
+        ctx.compute(L, L, 9, 64, y0=4, y1=11)
+    assert e.value.code == -2
+    with pytest.raises(despair.SadGpuError) as e:
+        ctx.compute(L, L, 9, 64, stream=99)
+    assert e.value.code == -2
+    big = np.zeros((3000, 10), np.uint8)
+    with pytest.raises(despair.SadGpuError) as e:
+        ctx.compute(big, big, 9, 64)
+    assert e.value.code == -2
+    with pytest.raises(despair.SadGpuError) as e:
+        ctx.wait(12345 << 16, L)
+    assert e.value.code == -4
