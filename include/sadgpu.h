@@ -60,8 +60,8 @@ typedef struct sadgpu_tuning {
     int rows_per_batch;     /* RB: rows staged through shared memory per iteration */
     int band_rows;          /* BH: output rows per CTA band                           */
     int groups_per_chunk;   /* disparity groups (4 disparities each) per CTA chunk     */
-    int kernel_variant;     /* 0 = auto, 1 = generic (shared-memory ring), 2 = register-ring fast path */
-    int reserved[4];
+    int kernel_variant;     /* 0 = auto, 1 = generic (shared-memory ring), 2 = register-ring fast path (block_size <= 15) */
+    int reserved[4];        /* reserved[0]: frames per launch, used by sadgpu_plan_describe only */
 } sadgpu_tuning;
 
 int  sadgpu_device_count(void);
@@ -106,6 +106,15 @@ int  sadgpu_compute_device(sadgpu_ctx *ctx, int device,
                            int w, int h, int block_size, int max_disparity, int y0, int y1,
                            uint8_t *dOut, size_t pitch_out, void *cuda_stream,
                            const sadgpu_tuning *tuning);
+
+/* Batch of n_frames frame pairs in ONE launch (video streams, BASELINE configs[4]): frame f lives at
+ * base + f*frame_stride (bytes).  Grid = strips x bands x frames, so the launch is many waves deep. */
+int  sadgpu_compute_device_batch(sadgpu_ctx *ctx, int device, int n_frames,
+                                 const uint8_t *dL, size_t pitch_l, size_t frame_stride_l,
+                                 const uint8_t *dR, size_t pitch_r, size_t frame_stride_r,
+                                 int w, int h, int block_size, int max_disparity, int y0, int y1,
+                                 uint8_t *dOut, size_t pitch_out, size_t frame_stride_out,
+                                 void *cuda_stream, const sadgpu_tuning *tuning);
 
 /* Pinned host memory from the context's pool: frames that already live here are uploaded
  * without the staging memcpy (cameras write straight into it). */

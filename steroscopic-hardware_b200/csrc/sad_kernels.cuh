@@ -255,13 +255,14 @@ __global__ void __launch_bounds__(256, 1) sad_generic_kernel(const SadArgs a)
 
 // Key map -> disparity bytes, used only when the disparity range was split over several CTAs.
 __global__ void sad_finalize_kernel(const uint32_t* __restrict__ gkey, uint8_t* __restrict__ out,
-                                    int W, int y0, int y1, int pitchOut, int D)
+                                    int W, int H, int y0, int y1, int pitchOut, long long frameOut, int D)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = y0 + blockIdx.y;
+    const int f = blockIdx.z;
     if (x < W && y < y1) {
-        const uint32_t d = gkey[(size_t)y * W + x] & 511u;
-        out[(size_t)y * pitchOut + x] = (uint8_t)((d * 255u) / (uint32_t)D);
+        const uint32_t d = gkey[((size_t)f * H + y) * W + x] & 511u;
+        out[(long long)f * frameOut + (size_t)y * pitchOut + x] = (uint8_t)((d * 255u) / (uint32_t)D);
     }
 }
 

@@ -3,6 +3,7 @@
 // compute entry point ends in a kernel launch or an error code.
 #include "../../include/sadgpu.h"
 #include "sad_kernels.cuh"
+#include "sad_fast.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -128,6 +129,97 @@ const launch_fn kLaunchGeneric[16] = {
     launch_generic<8>, launch_generic<9>, launch_generic<10>, launch_generic<11>,
     launch_generic<12>, launch_generic<13>, launch_generic<14>, launch_generic<15>};
 
+
+// ---------------------------------------------------------------------------------------
+// Fast path (sad_fast.cuh): block_size <= 15.  Template instance = (h, groups per chunk).
+// ---------------------------------------------------------------------------------------
+struct FastPlan {
+    FastArgs a;
+    dim3 grid;
+    int nthreads;
+    size_t smem;
+    int half, ngc, rb;
+    int launches;
+};
+
+template <int HALF, int NGC>
+cudaError_t launch_fast(const FastPlan& p, cudaStream_t s, bool* attr_done)
+{
+    using C = FastCfg<HALF, NGC>;
+    static_assert(C::SMEM <= kSmemBudget, "fast kernel does not fit shared memory");
+    auto k = sad_fast_kernel<HALF, NGC>;
+    if (!*attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return e;
+        *attr_done = true;
+    }
+    k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    return cudaGetLastError();
+}
+
+typedef cudaError_t (*fast_fn)(const FastPlan&, cudaStream_t, bool*);
+struct FastEntry { fast_fn fn; int nt, smem, rb; };
+template <int HALF, int NGC> constexpr FastEntry fast_entry()
+{
+    return FastEntry{launch_fast<HALF, NGC>, FastCfg<HALF, NGC>::NT, FastCfg<HALF, NGC>::SMEM, FastCfg<HALF, NGC>::RB};
+}
+// index [half][slot], slot 0/1/2 = 9/17/33 groups per chunk; h >= 5 has no 33-group instance (shared memory)
+const int kFastNgc[3] = {9, 17, 33};
+const FastEntry kFast[8][3] = {
+    {fast_entry<0, 9>(), fast_entry<0, 17>(), fast_entry<0, 33>()},
+    {fast_entry<1, 9>(), fast_entry<1, 17>(), fast_entry<1, 33>()},
+    {fast_entry<2, 9>(), fast_entry<2, 17>(), fast_entry<2, 33>()},
+    {fast_entry<3, 9>(), fast_entry<3, 17>(), fast_entry<3, 33>()},
+    {fast_entry<4, 9>(), fast_entry<4, 17>(), fast_entry<4, 33>()},
+    {fast_entry<5, 9>(), fast_entry<5, 17>(), FastEntry{nullptr, 0, 0, 0}},
+    {fast_entry<6, 9>(), fast_entry<6, 17>(), FastEntry{nullptr, 0, 0, 0}},
+    {fast_entry<7, 9>(), fast_entry<7, 17>(), FastEntry{nullptr, 0, 0, 0}}};
+
+bool fast_supported(int B) { return B / 2 <= 7; }
+
+int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, const sadgpu_tuning* t, int sm_count,
+                   FastPlan* p, int* slot_out)
+{
+    int rc = validate(w, h, B, D, y0, y1);
+    if (rc) return rc;
+    if (!fast_supported(B) || n_frames < 1) return SADGPU_EINVAL;
+    const int half = B / 2;
+    FastArgs& a = p->a;
+    memset(&a, 0, sizeof(a));
+    a.W = w; a.H = h; a.y0 = y0; a.y1 = y1; a.D = D;
+    a.NG = (D + 4) / 4;
+    int slot = a.NG <= 9 ? 0 : a.NG <= 17 ? 1 : 2;
+    if (!kFast[half][slot].fn) slot = 1;
+    if (t && t->groups_per_chunk > 0) {                     // tests: force smaller chunks
+        slot = t->groups_per_chunk <= 9 ? 0 : t->groups_per_chunk <= 17 ? 1 : slot;
+    }
+    const FastEntry& fe = kFast[half][slot];
+    p->half = half; p->ngc = kFastNgc[slot]; p->rb = fe.rb;
+    a.NC = ceil_div(a.NG, p->ngc);
+    p->nthreads = fe.nt; p->smem = fe.smem;
+    const int rows = std::max(1, y1 - y0);
+    const int nstrips = ceil_div(w, 64);
+    int nbands = 1;
+    if (t && t->band_rows > 0) {
+        a.BH = std::min(std::max(1, t->band_rows), rows);
+    } else {
+        long best_cost = -1;
+        for (int nb = 1; nb <= std::min(rows, 64); ++nb) {
+            const int bh = ceil_div(rows, nb);
+            const long ctas = (long)nstrips * nb * a.NC * n_frames;
+            const long waves = (ctas + sm_count - 1) / sm_count;
+            const long cost = waves * (round_up(bh + 2 * half, fe.rb) + fe.rb / 2 + 2);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; nbands = nb; }
+        }
+        a.BH = ceil_div(rows, nbands);
+    }
+    nbands = ceil_div(rows, a.BH);
+    p->grid = dim3(nstrips, nbands, a.NC * n_frames);
+    p->launches = a.NC == 1 ? 1 : 3;
+    *slot_out = slot;
+    return SADGPU_OK;
+}
+
 struct Slot {
     int dev_index = 0, device = 0;
     cudaStream_t st = nullptr;
@@ -154,6 +246,8 @@ struct sadgpu_ctx {
     std::mutex pool_mu;
     std::vector<std::pair<uint8_t*, size_t>> pool;
     bool attr_done[kMaxDevices][16];
+    bool fast_attr_done[kMaxDevices][8][3];
+    std::vector<size_t> dev_gkey_bytes;
     std::vector<uint32_t*> dev_gkey;       // per device scratch for sadgpu_compute_device
     std::mutex dev_mu;
 };
@@ -169,25 +263,87 @@ bool in_pool(sadgpu_ctx* c, const void* p, size_t bytes)
     return false;
 }
 
-// Enqueue fill (if chunked) + kernel + finalize (if chunked) on stream s.  Device must be current.
-int enqueue(sadgpu_ctx* c, int dev_index, const Plan& pl, uint32_t* gkey, cudaStream_t s)
+struct Job {
+    const uint8_t* dL; size_t pitchL; long long frameL;
+    const uint8_t* dR; size_t pitchR; long long frameR;
+    uint8_t* dOut; size_t pitchOut; long long frameOut;
+    int n_frames, w, h, B, D, y0, y1;
+};
+
+// Grows the per-device key-map scratch (only needed when the disparity range is chunked).
+int ensure_gkey(sadgpu_ctx* c, int dev_index, size_t bytes, uint32_t** out)
 {
-    Plan p = pl;
-    if (p.a.NC > 1) {
-        if (!gkey) return SADGPU_EINVAL;
-        p.a.gkey = gkey;
-        const size_t n = (size_t)p.a.W * (p.a.y1 - p.a.y0);
-        sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, s>>>(gkey + (size_t)p.a.y0 * p.a.W, n, 0xFFFFFFFFu);
+    std::lock_guard<std::mutex> g(c->dev_mu);
+    if (c->dev_gkey_bytes[dev_index] < bytes) {
+        if (c->dev_gkey[dev_index]) { cudaDeviceSynchronize(); cudaFree(c->dev_gkey[dev_index]); c->dev_gkey[dev_index] = nullptr; }
+        cudaError_t e = cudaMalloc((void**)&c->dev_gkey[dev_index], bytes);
+        if (e != cudaSuccess) { c->dev_gkey_bytes[dev_index] = 0; return (int)e; }
+        c->dev_gkey_bytes[dev_index] = bytes;
     }
-    cudaError_t e = kLaunchGeneric[p.half](p, s, &c->attr_done[dev_index][p.half]);
-    if (e != cudaSuccess) return (int)e;
-    if (p.a.NC > 1) {
-        dim3 g(ceil_div(p.a.W, 256), p.a.y1 - p.a.y0);
-        sad_finalize_kernel<<<g, 256, 0, s>>>(gkey, p.a.out, p.a.W, p.a.y0, p.a.y1, p.a.pitchOut, p.a.D);
-        e = cudaGetLastError();
+    *out = c->dev_gkey[dev_index];
+    return SADGPU_OK;
+}
+
+// Enqueue one job (one frame, or a batch of frames) on stream s.  The device must be current.
+// Chooses the fast path (block_size <= 15) or the generic kernel; never a CPU path.
+int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, uint32_t* slot_gkey, cudaStream_t s)
+{
+    const int variant = t ? t->kernel_variant : 0;
+    if (variant < 0 || variant > 2) return SADGPU_EINVAL;
+    if (variant == 2 && !fast_supported(j.B)) return SADGPU_EINVAL;
+    const bool use_fast = variant == 2 || (variant == 0 && fast_supported(j.B));
+    int launches = 0;
+    if (use_fast) {
+        FastPlan p; int slot = 0;
+        int rc = make_fast_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, j.n_frames, t, c->sm_count[dev_index], &p, &slot);
+        if (rc) return rc;
+        if (j.y1 == j.y0) return SADGPU_OK;
+        FastArgs& a = p.a;
+        a.L = j.dL; a.R = j.dR; a.out = j.dOut;
+        a.pitchL = (int)j.pitchL; a.pitchR = (int)j.pitchR; a.pitchOut = (int)j.pitchOut;
+        a.frameL = j.frameL; a.frameR = j.frameR; a.frameOut = j.frameOut;
+        a.aligned = ((uintptr_t)j.dR % 4 == 0 && j.pitchR % 4 == 0 && j.frameR % 4 == 0) ? 1 : 0;
+        if (a.NC > 1) {
+            const size_t n = (size_t)j.n_frames * j.w * j.h;
+            uint32_t* gk = slot_gkey;
+            if (!gk || j.n_frames > 1) { rc = ensure_gkey(c, dev_index, n * sizeof(uint32_t), &gk); if (rc) return rc; }
+            a.gkey = gk;
+            sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 8192), 256, 0, s>>>(gk, n, 0xFFFFFFFFu);
+        }
+        cudaError_t e = kFast[p.half][slot].fn(p, s, &c->fast_attr_done[dev_index][p.half][slot]);
         if (e != cudaSuccess) return (int)e;
+        if (a.NC > 1) {
+            dim3 g(ceil_div(j.w, 256), j.y1 - j.y0, j.n_frames);
+            sad_finalize_kernel<<<g, 256, 0, s>>>(a.gkey, j.dOut, j.w, j.h, j.y0, j.y1, (int)j.pitchOut, j.frameOut, j.D);
+            if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+        }
+        launches = p.launches;
+    } else {
+        Plan p;
+        int rc = make_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, t, c->sm_count[dev_index], &p);
+        if (rc) return rc;
+        if (j.y1 == j.y0) return SADGPU_OK;
+        uint32_t* gk = slot_gkey;
+        if (p.a.NC > 1 && !gk) { rc = ensure_gkey(c, dev_index, (size_t)j.w * j.h * sizeof(uint32_t), &gk); if (rc) return rc; }
+        for (int f = 0; f < j.n_frames; ++f) {
+            p.a.L = j.dL + f * j.frameL; p.a.R = j.dR + f * j.frameR; p.a.out = j.dOut + f * j.frameOut;
+            p.a.pitchL = (int)j.pitchL; p.a.pitchR = (int)j.pitchR; p.a.pitchOut = (int)j.pitchOut;
+            if (p.a.NC > 1) {
+                p.a.gkey = gk;
+                const size_t n = (size_t)j.w * j.h;
+                sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, s>>>(gk, n, 0xFFFFFFFFu);
+            }
+            cudaError_t e = kLaunchGeneric[p.half](p, s, &c->attr_done[dev_index][p.half]);
+            if (e != cudaSuccess) return (int)e;
+            if (p.a.NC > 1) {
+                dim3 g(ceil_div(j.w, 256), j.y1 - j.y0, 1);
+                sad_finalize_kernel<<<g, 256, 0, s>>>(gk, p.a.out, j.w, j.h, j.y0, j.y1, (int)j.pitchOut, 0, j.D);
+                if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+            }
+            launches += p.launches;
+        }
     }
-    c->last_launches.store(p.launches);
+    c->last_launches.store(launches);
     return SADGPU_OK;
 }
 
@@ -223,17 +379,15 @@ int submit_locked(sadgpu_ctx* c, Slot* s, const uint8_t* l, int ls, const uint8_
 {
     cudaError_t e = cudaSetDevice(s->device);
     if (e != cudaSuccess) return (int)e;
-    Plan p;
-    int rc = make_plan(w, h, B, D, y0, y1, nullptr, c->sm_count[s->dev_index], &p);
+    int rc = validate(w, h, B, D, y0, y1);
     if (rc) return rc;
     const int half = B / 2;
     const int ys = std::max(0, y0 - half), ye = std::min(h, y1 + half);
     if ((rc = upload(c, s, l, ls, s->hL, s->dL, w, ys, ye))) return rc;
     if ((rc = upload(c, s, r, rs, s->hR, s->dR, w, ys, ye))) return rc;
-    p.a.L = s->dL; p.a.R = s->dR; p.a.out = s->dOut;
-    p.a.pitchL = p.a.pitchR = p.a.pitchOut = (int)s->pitch;
     if (y1 > y0) {
-        if ((rc = enqueue(c, s->dev_index, p, s->gkey, s->st))) return rc;
+        Job j{s->dL, s->pitch, 0, s->dR, s->pitch, 0, s->dOut, s->pitch, 0, 1, w, h, B, D, y0, y1};
+        if ((rc = run_job(c, s->dev_index, j, nullptr, s->gkey, s->st))) return rc;
         s->out_direct = direct_out != nullptr;
         uint8_t* dst = direct_out ? direct_out + (size_t)y0 * direct_stride : s->hOut + (size_t)y0 * s->pitch;
         const size_t dpitch = direct_out ? (size_t)direct_stride : s->pitch;
@@ -296,6 +450,7 @@ int sadgpu_create(const int* devices, int n_devices, int max_w, int max_h, int n
     sadgpu_ctx* c = new (std::nothrow) sadgpu_ctx();
     if (!c) return SADGPU_ENOMEM;
     memset(c->attr_done, 0, sizeof(c->attr_done));
+    memset(c->fast_attr_done, 0, sizeof(c->fast_attr_done));
     c->max_w = max_w; c->max_h = max_h;
     for (int i = 0; i < n_devices; ++i) {
         const int d = devices ? devices[i] : i;
@@ -307,6 +462,7 @@ int sadgpu_create(const int* devices, int n_devices, int max_w, int max_h, int n
         c->sm_count.push_back(prop.multiProcessorCount);
     }
     c->dev_gkey.assign(n_devices, nullptr);
+    c->dev_gkey_bytes.assign(n_devices, 0);
     const size_t pitch = (size_t)round_up(max_w, 256);
     const size_t img = pitch * (size_t)max_h;
     for (int i = 0; i < n_streams; ++i) {
@@ -411,32 +567,31 @@ int sadgpu_compute_sharded(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_
     return first_err;
 }
 
+int sadgpu_compute_device_batch(sadgpu_ctx* c, int device, int n_frames,
+                                const uint8_t* dL, size_t pitch_l, size_t frame_stride_l,
+                                const uint8_t* dR, size_t pitch_r, size_t frame_stride_r,
+                                int w, int h, int B, int D, int y0, int y1,
+                                uint8_t* dOut, size_t pitch_out, size_t frame_stride_out,
+                                void* cuda_stream, const sadgpu_tuning* tuning)
+{
+    if (!c || !dL || !dR || !dOut || n_frames < 1) return SADGPU_EINVAL;
+    if (device < 0 || device >= (int)c->devices.size()) return SADGPU_ERANGE;
+    if (pitch_l < (size_t)w || pitch_r < (size_t)w || pitch_out < (size_t)w) return SADGPU_EINVAL;
+    int rc = validate(w, h, B, D, y0, y1);
+    if (rc) return rc;
+    cudaError_t e = cudaSetDevice(c->devices[device]);
+    if (e != cudaSuccess) return (int)e;
+    Job j{dL, pitch_l, (long long)frame_stride_l, dR, pitch_r, (long long)frame_stride_r,
+          dOut, pitch_out, (long long)frame_stride_out, n_frames, w, h, B, D, y0, y1};
+    return run_job(c, device, j, tuning, nullptr, (cudaStream_t)cuda_stream);
+}
+
 int sadgpu_compute_device(sadgpu_ctx* c, int device, const uint8_t* dL, size_t pitch_l, const uint8_t* dR, size_t pitch_r,
                           int w, int h, int B, int D, int y0, int y1, uint8_t* dOut, size_t pitch_out,
                           void* cuda_stream, const sadgpu_tuning* tuning)
 {
-    if (!c || !dL || !dR || !dOut) return SADGPU_EINVAL;
-    if (device < 0 || device >= (int)c->devices.size()) return SADGPU_ERANGE;
-    if (pitch_l < (size_t)w || pitch_r < (size_t)w || pitch_out < (size_t)w) return SADGPU_EINVAL;
-    Plan p;
-    int rc = make_plan(w, h, B, D, y0, y1, tuning, c->sm_count[device], &p);
-    if (rc) return rc;
-    if (y1 == y0) return SADGPU_OK;
-    cudaError_t e = cudaSetDevice(c->devices[device]);
-    if (e != cudaSuccess) return (int)e;
-    uint32_t* gkey = nullptr;
-    if (p.a.NC > 1) {
-        if (w > c->max_w || h > c->max_h) return SADGPU_ERANGE;
-        std::lock_guard<std::mutex> g(c->dev_mu);
-        if (!c->dev_gkey[device]) {
-            e = cudaMalloc((void**)&c->dev_gkey[device], (size_t)c->max_w * c->max_h * sizeof(uint32_t));
-            if (e != cudaSuccess) return (int)e;
-        }
-        gkey = c->dev_gkey[device];
-    }
-    p.a.L = dL; p.a.R = dR; p.a.out = dOut;
-    p.a.pitchL = (int)pitch_l; p.a.pitchR = (int)pitch_r; p.a.pitchOut = (int)pitch_out;
-    return enqueue(c, device, p, gkey, (cudaStream_t)cuda_stream);
+    return sadgpu_compute_device_batch(c, device, 1, dL, pitch_l, 0, dR, pitch_r, 0, w, h, B, D, y0, y1,
+                                       dOut, pitch_out, 0, cuda_stream, tuning);
 }
 
 void* sadgpu_host_alloc(sadgpu_ctx* c, size_t bytes)
@@ -461,6 +616,20 @@ int sadgpu_last_launch_count(sadgpu_ctx* c) { return c ? c->last_launches.load()
 
 int sadgpu_plan_describe(int w, int h, int B, int D, int y0, int y1, const sadgpu_tuning* t, char* buf, size_t buflen)
 {
+    const int variant = t ? t->kernel_variant : 0;
+    if (variant == 2 || (variant == 0 && fast_supported(B))) {
+        FastPlan p; int slot = 0;
+        const int nf = t && t->reserved[0] > 0 ? t->reserved[0] : 1;       // reserved[0]: frames per launch (describe only)
+        int rc = make_fast_plan(w, h, B, D, y0, y1, nf, t, 148, &p, &slot);
+        if (rc) return rc;
+        if (buf && buflen)
+            snprintf(buf, buflen,
+                     "{\"variant\":\"fast\",\"half\":%d,\"NG\":%d,\"NC\":%d,\"NGc\":%d,\"TW\":64,\"RB\":%d,\"BH\":%d,"
+                     "\"grid\":[%u,%u,%u],\"threads\":%d,\"smem\":%zu,\"launches\":%d,\"frames_per_launch\":%d}",
+                     p.half, p.a.NG, p.a.NC, p.ngc, p.rb, p.a.BH, p.grid.x, p.grid.y, p.grid.z, p.nthreads, p.smem,
+                     p.launches, nf);
+        return SADGPU_OK;
+    }
     Plan p;
     int rc = make_plan(w, h, B, D, y0, y1, t, 148, &p);
     if (rc) return rc;

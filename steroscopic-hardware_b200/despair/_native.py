@@ -31,6 +31,9 @@ EXPORTS = {
     "sadgpu_compute_device": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int,
                                       c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p,
                                       ctypes.POINTER(Tuning)]),
+    "sadgpu_compute_device_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_size_t, c_void_p, c_size_t,
+                                            c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
+                                            c_size_t, c_void_p, ctypes.POINTER(Tuning)]),
     "sadgpu_host_alloc": (c_void_p, [c_void_p, c_size_t]),
     "sadgpu_host_free": (None, [c_void_p, c_void_p]),
     "sadgpu_last_launch_count": (c_int, [c_void_p]),

@@ -90,6 +90,17 @@ class Context:
         N.check(self._L.sadgpu_compute_device(self._h, device, dL, pitch_l, dR, pitch_r, w, h, block_size,
                                                max_disparity, y0, y1, dOut, pitch_out, cuda_stream, tp))
 
+    def compute_device_batch(self, n_frames, dL, pitch_l, fs_l, dR, pitch_r, fs_r, w, h, block_size, max_disparity,
+                             dOut, pitch_out, fs_out, y0=0, y1=None, device=0, cuda_stream=0, tuning=None):
+        y1 = h if y1 is None else y1
+        tp = None
+        if tuning:
+            t = N.Tuning(); [setattr(t, k, v) for k, v in tuning.items()]
+            tp = ctypes.byref(t)
+        N.check(self._L.sadgpu_compute_device_batch(self._h, device, n_frames, dL, pitch_l, fs_l, dR, pitch_r, fs_r,
+                                                     w, h, block_size, max_disparity, y0, y1, dOut, pitch_out, fs_out,
+                                                     cuda_stream, tp))
+
     # -- pinned pool -----------------------------------------------------------------------
     def host_array(self, shape):
         n = int(np.prod(shape))
@@ -104,12 +115,13 @@ class Context:
         return self._L.sadgpu_last_launch_count(self._h)
 
 
-def plan_describe(w, h, block_size, max_disparity, y0=0, y1=None, tuning=None):
+def plan_describe(w, h, block_size, max_disparity, y0=0, y1=None, tuning=None, frames=1):
     y1 = h if y1 is None else y1
     buf = ctypes.create_string_buffer(1024)
-    tp = None
-    if tuning:
-        t = N.Tuning(); [setattr(t, k, v) for k, v in tuning.items()]
-        tp = ctypes.byref(t)
+    t = N.Tuning()
+    for k, v in (tuning or {}).items():
+        setattr(t, k, v)
+    t.reserved[0] = frames
+    tp = ctypes.byref(t)
     N.check(N.lib().sadgpu_plan_describe(w, h, block_size, max_disparity, y0, y1, tp, buf, 1024))
     return json.loads(buf.value.decode())

@@ -36,6 +36,8 @@ def main():
         exp = O.frame_box(L, R, B, D)
         tun = None
         if i % 3 == 1: tun = dict(rows_per_batch=int(rng.integers(1, 9)), band_rows=int(rng.integers(1, 40)), groups_per_chunk=int(rng.integers(1, 21)))
+        if B <= 15 and i % 2 == 0:
+            tun = dict(tun or {}); tun['kernel_variant'] = 2
         got = dev_run(ctx, L, R, B, D, tun)
         ncase += 1
         if not np.array_equal(got, exp):
@@ -71,6 +73,19 @@ def main():
         print(f"1080p B={B} D={D}: {ms*1e3:.1f} us/frame  {ev/ms/1e9:.3f} Tevals/s  plan={json.dumps(despair.plan_describe(Ww, Hh, B, D))}")
         exp = O.frame_box(Ls, Rs, B, D, 500, 516)
         print("   parity rows 500..516:", np.array_equal(dO.cpu().numpy()[500:516], exp))
+        if B <= 15:
+            F = 16
+            bL = dL.unsqueeze(0).repeat(F, 1, 1).contiguous(); bR = dR.unsqueeze(0).repeat(F, 1, 1).contiguous(); bO = torch.zeros_like(bL)
+            fs = Hh * Ww
+            run = lambda: ctx.compute_device_batch(F, bL.data_ptr(), Ww, fs, bR.data_ptr(), Ww, fs, Ww, Hh, B, D, bO.data_ptr(), Ww, fs, cuda_stream=st)
+            for _ in range(2): run()
+            e0.record()
+            for _ in range(5): run()
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / (5 * F)
+            print(f"   batch16: {ms*1e3:.1f} us/frame  {ev/ms/1e9:.3f} Tevals/s  plan={json.dumps(despair.plan_describe(Ww, Hh, B, D, frames=F))}")
+            ok = all(np.array_equal(bO[f].cpu().numpy()[500:516], exp) for f in (0, F - 1))
+            print("   batch parity:", ok, " full-frame equal to single:", bool(torch.equal(bO[3], dO)))
 
 if __name__ == "__main__":
     main()
