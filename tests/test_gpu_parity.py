@@ -87,8 +87,35 @@ def test_tilings_do_not_change_pixels(torch_mod, ctx, oracle):
         B = int(rng.integers(1, 32)); D = int(rng.choice([5, 16, 64, 128, 256]))
         L, R = synth_pair(rng, H, W, i % 5)
         tun = dict(rows_per_batch=int(rng.integers(1, 12)), band_rows=int(rng.integers(1, 50)),
-                   groups_per_chunk=int(rng.integers(1, 21)))
+                   groups_per_chunk=int(rng.integers(1, 21)), kernel_variant=1 if (i % 2 or B > 15) else 2)
         assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, tun), oracle.frame_box(L, R, B, D)), (W, H, B, D, tun)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_both_kernel_variants_agree_with_oracle(torch_mod, ctx, oracle, variant):
+    """variant 1 = generic shared-memory-ring kernel (any block size), 2 = register-ring fast path (B <= 15)."""
+    rng = np.random.default_rng(60 + variant)
+    for i in range(24):
+        W = int(rng.integers(20, 400)); H = int(rng.integers(10, 100))
+        B = int(rng.integers(1, 16)); D = int(rng.choice([7, 16, 33, 64, 128, 200, 256]))
+        L, R = synth_pair(rng, H, W, i % 5)
+        got = dev_run(torch_mod, ctx, L, R, B, D, dict(kernel_variant=variant))
+        assert np.array_equal(got, oracle.frame_box(L, R, B, D)), (W, H, B, D, variant)
+
+
+def test_batched_frames_one_launch(torch_mod, ctx, oracle):
+    torch = torch_mod
+    rng = np.random.default_rng(61)
+    for (F, H, W, B, D) in [(5, 60, 200, 9, 128), (3, 40, 130, 15, 256), (4, 33, 70, 31, 64)]:
+        pairs = [synth_pair(rng, H, W, k % 5) for k in range(F)]
+        dL = torch.from_numpy(np.stack([p[0] for p in pairs])).cuda(); dR = torch.from_numpy(np.stack([p[1] for p in pairs])).cuda()
+        dO = torch.zeros_like(dL)
+        ctx.compute_device_batch(F, dL.data_ptr(), W, W * H, dR.data_ptr(), W, W * H, W, H, B, D, dO.data_ptr(), W, W * H,
+                                 cuda_stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        got = dO.cpu().numpy()
+        for k in range(F):
+            assert np.array_equal(got[k], oracle.frame_box(pairs[k][0], pairs[k][1], B, D)), (k, H, W, B, D)
 
 
 def test_row_ranges_pitch_and_untouched_rows(torch_mod, ctx, oracle):
