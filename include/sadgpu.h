@@ -60,7 +60,8 @@ typedef struct sadgpu_tuning {
     int rows_per_batch;     /* RB: rows staged through shared memory per iteration */
     int band_rows;          /* BH: output rows per CTA band                           */
     int groups_per_chunk;   /* disparity groups (4 disparities each) per CTA chunk     */
-    int kernel_variant;     /* 0 = auto, 1 = generic (shared-memory ring), 2 = register-ring fast path (block_size <= 15) */
+    int kernel_variant;     /* 0 = auto, 1 = generic (any block size), 2 = register-ring fast path (block_size <= 15),
+                               3 = warp-specialised fast path (block_size <= 9, max_disparity > 64) */
     int reserved[4];        /* reserved[0]: frames per launch, used by sadgpu_plan_describe only */
 } sadgpu_tuning;
 

@@ -22,6 +22,7 @@ struct FastArgs {
     int W, H, y0, y1;
     int D, NG, NC, BH;
     int aligned;                             // R rows may be fetched with aligned 32-bit loads
+    unsigned k65536;                         // = 65536, passed at run time so that v*65536+idx stays an IMAD (FMA pipe)
 };
 
 template <int HALF> struct FastTraits {
@@ -31,7 +32,6 @@ template <int HALF> struct FastTraits {
     static constexpr int NSTEP = TW + 2 * HALF;                     // phase-A walk length
     static constexpr int LW = (NSTEP + 3) & ~3;                     // words per replicated-L row
     static constexpr int RB = WIN >= 7 ? WIN : WIN * ((8 + WIN - 1) / WIN);   // rows per batch (multiple of WIN)
-    static constexpr int GT = HALF <= 4 ? 4 : 2;                    // groups per phase-B thread
     static constexpr bool BIAS = WIN * WIN * 255 + 32768 < 65536;   // h <= 5
     static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;         // byte phase of the R walk in its aligned word
     static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;     // aligned R words one walk touches
@@ -39,11 +39,13 @@ template <int HALF> struct FastTraits {
 
 template <int HALF, int NGC> struct FastCfg : FastTraits<HALF> {
     using T = FastTraits<HALF>;
-    static constexpr int K = (NGC + T::GT - 1) / T::GT;             // phase-B threads per column
-    static constexpr int NGP = K * T::GT;                           // group slots in H
+    // groups per phase-B thread: bounded by the register ring (2*GT*WIN registers)
+    static constexpr int GT = HALF <= 4 ? (NGC == 33 ? 5 : 3) : 2;
+    static constexpr int K = (NGC + GT - 1) / GT;                   // phase-B threads per column
+    static constexpr int NGP = K * GT;                              // group slots in H
     static constexpr int NT = T::TW * K;                            // threads per CTA
     static constexpr int RW = NGC - 1 + T::NWALKW;                  // words per aligned-R row
-    static constexpr int H_BYTES = T::RB * NGP * T::TWP * 8;
+    static constexpr int H_BYTES = ((T::RB * NGP * T::TWP * 8 + 15) / 16) * 16;
     static constexpr int L_BYTES = T::RB * T::LW * 4;
     static constexpr int R_BYTES = T::RB * RW * 4;
     static constexpr int PK_BYTES = T::RB * K * T::TW * 4;
@@ -54,6 +56,13 @@ template <int HALF, int NGC> struct FastCfg : FastTraits<HALF> {
     static constexpr int OFF_LUT = OFF_PK + PK_BYTES;
     static constexpr int SMEM = OFF_LUT + LUT_BYTES;
 };
+
+// Keys (sum << 16 | index).  Low lane: one IMAD (FMA pipe) with the multiplier 65536 held in a register and the
+// index as immediate addend; high lane: one LOP3 (ALU pipe), (v & mask) | index, mask held in a register.
+// Both constants are made opaque so that ptxas keeps them in registers instead of re-materialising them.
+__device__ __forceinline__ uint32_t opaque(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
+__device__ __forceinline__ uint32_t key_lo(uint32_t v, uint32_t k65536, uint32_t idx) { return v * k65536 + idx; }
+__device__ __forceinline__ uint32_t key_hi(uint32_t v, uint32_t maskhi, uint32_t idx) { return (v & maskhi) | idx; }
 
 // ---- phase A: one (row, group) walk, fully unrolled --------------------------------------
 template <int HALF, bool EDGE>
@@ -131,6 +140,7 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
         for (int r = 0; r < WIN; ++r) { ringE[r][j] = 0; ringO[r][j] = 0; }
     }
     const uint32_t keybase = 4u * (uint32_t)(g0 + kB * GT);
+    const uint32_t k16 = opaque(a.k65536), mhi = opaque(a.k65536 * 0xFFFFu);      // 65536, 0xFFFF0000
 
     const int r0 = yb0 - HALF;
     const int nrows = (yb1 - yb0) + 2 * HALF;
@@ -216,10 +226,10 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
                     for (int j = 0; j < GT; ++j) {
                         const uint32_t ve = C::BIAS ? VE[j] : (VE[j] | mE[j]);
                         const uint32_t vo = C::BIAS ? VO[j] : (VO[j] | mO[j]);
-                        const uint32_t kEl = (ve << 16) | (4u * j + 3u);
-                        const uint32_t kEh = (ve & 0xFFFF0000u) | (4u * j + 1u);
-                        const uint32_t kOl = (vo << 16) | (4u * j + 2u);
-                        const uint32_t kOh = (vo & 0xFFFF0000u) | (4u * j + 0u);
+                        const uint32_t kEl = key_lo(ve, k16, 4u * j + 3u);
+                        const uint32_t kEh = key_hi(ve, mhi, 4u * j + 1u);
+                        const uint32_t kOl = key_lo(vo, k16, 4u * j + 2u);
+                        const uint32_t kOh = key_hi(vo, mhi, 4u * j + 0u);
                         best = min(best, min(kEl, kEh));
                         best = min(best, min(kOl, kOh));
                     }

@@ -1,0 +1,262 @@
+// sad_ws.cuh — warp-specialised, double-buffered variant of the fast path (block_size <= 9, chunks of
+// 33 disparity groups = 132 disparity slots, i.e. max_disparity 65..128 in one chunk, up to 256 in two).
+//
+// Same arithmetic as sad_fast.cuh; the difference is scheduling.  A CTA owns a 32-column strip and has
+// 24 warps with FIXED roles (no phase alternation, one __syncthreads per 9-row batch), registers rebalanced
+// between the roles with setmaxnreg:
+//   warps 0..8   walkers: warp w walks row w of the batch for 32 disparity groups (lanes = groups),
+//                horizontal running window sums -> H[buf][row][group][column] in shared memory;
+//   warp  9      walks the 33rd group (the single candidate d = 128 when D = 128), one lane per row;
+//   warps 10,11  prefetch the next batch's L/R tiles into the other tile buffer;
+//   warps 12..22 consumers: warp 12+k owns groups 3k..3k+2 for 32 columns (lanes = columns): vertical
+//                running sums with the previous 2h+1 rows in a register ring, key-min argmin, partial
+//                best -> pk; then the cross-warp min + LUT + store of the batch before.
+//   warp  23     finisher: min over the 11 partial keys of a pixel, d*255/D LUT, store.
+// Producers work on batch i while consumers work on batch i-1 (H and tiles are double-buffered).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "sad_fast.cuh"
+
+namespace sadgpu {
+
+template <int HALF> struct WsCfg {
+    static constexpr int WIN = 2 * HALF + 1;
+    static constexpr int TW = 32, TWP = 33;
+    static constexpr int NSTEP = TW + 2 * HALF;
+    static constexpr int LW = (NSTEP + 3) & ~3;
+    static constexpr int RB = 9;                       // rows per batch = row-walker warps = ring length
+    static constexpr int NGC = 33, GT = 3, K = 11;     // groups per chunk, groups per consumer thread, consumer warps
+    // warp roles (6 warpgroups of 4 warps): producers = warps 0..11, consumers = warps 12..23
+    static constexpr int W_TAIL = RB;                  // warp 9: 33rd group, one lane per row
+    static constexpr int W_LOAD = 10;                  // warps 10,11: tile prefetch
+    static constexpr int W_CONS = 12;                  // warps 12..22: consumer k = warp-12
+    static constexpr int W_FIN = W_CONS + K;           // warp 23: cross-warp min + LUT + store
+    static constexpr int NT = 768;
+    static constexpr int REGS_LAUNCH = 80, REGS_PROD = 56, REGS_CONS = 104;   // setmaxnreg moves registers inside the CTA's launch allocation
+    static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
+    static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;
+    static constexpr int RW = NGC - 1 + NWALKW;
+    static constexpr int H_BYTES = ((RB * NGC * TWP * 8 + 15) / 16) * 16;      // one buffer
+    static constexpr int L_BYTES = RB * LW * 4;
+    static constexpr int R_BYTES = ((RB * RW * 4 + 15) / 16) * 16;
+    static constexpr int PK_BYTES = RB * K * TW * 4;
+    static constexpr int OFF_L = 2 * H_BYTES;
+    static constexpr int OFF_R = OFF_L + 2 * L_BYTES;
+    static constexpr int OFF_PK = OFF_R + 2 * R_BYTES;
+    static constexpr int OFF_LUT = OFF_PK + 2 * PK_BYTES;
+    static constexpr int SMEM = OFF_LUT + 1040;
+    static_assert(WIN <= RB, "register ring shorter than the window");
+    static_assert(NT * REGS_LAUNCH <= 65536 && 384 * REGS_PROD + 384 * REGS_CONS <= NT * REGS_LAUNCH, "register budget");
+    static_assert(GT * K == NGC && W_FIN == 23, "warp roles");
+};
+
+// One (row, group) walk: TW outputs, NSTEP steps, fully unrolled (see fast_walk in sad_fast.cuh).
+template <int HALF, bool EDGE>
+__device__ __forceinline__ void ws_walk(const uint32_t* __restrict__ Lr, const uint32_t* __restrict__ Rr,
+                                        uint2* __restrict__ Hout, int nvalid)
+{
+    using T = WsCfg<HALF>;
+    uint32_t e[T::NSTEP], o[T::NSTEP];
+    uint32_t hE = 0, hO = 0, w0 = 0, w1 = 0;
+    uint4 lv = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < T::NSTEP; ++i) {
+        if ((i & 3) == 0) lv = *reinterpret_cast<const uint4*>(Lr + i);
+        const int bi = i + T::OFF;
+        if (i == 0) { w0 = Rr[bi >> 2]; w1 = Rr[(bi >> 2) + 1]; }
+        else if ((bi & 3) == 0) { w0 = w1; w1 = Rr[(bi >> 2) + 1]; }
+        const uint32_t lw = (i & 3) == 0 ? lv.x : (i & 3) == 1 ? lv.y : (i & 3) == 2 ? lv.z : lv.w;
+        const uint32_t rw = (bi & 3) == 0 ? w0 : __funnelshift_r(w0, w1, 8 * (bi & 3));
+        uint32_t ad = __vabsdiffu4(lw, rw);
+        if (EDGE) ad = (i < nvalid) ? ad : 0u;
+        e[i] = __byte_perm(ad, 0u, 0x4240);
+        o[i] = __byte_perm(ad, 0u, 0x4341);
+        if (i >= T::WIN) { hE = hE + e[i] - e[i - T::WIN]; hO = hO + o[i] - o[i - T::WIN]; }
+        else             { hE += e[i]; hO += o[i]; }
+        if (i >= 2 * HALF) Hout[i - 2 * HALF] = make_uint2(hE, hO);
+    }
+}
+
+// Consumer warp: NGB groups (20 or 12 disparities) x 32 columns; one barrier per batch.
+template <int HALF, int NGB>
+__device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __restrict__ Hs, uint32_t* __restrict__ pk,
+                                           int kB, int lane, int x0, int g0, int r0, int nb)
+{
+    using C = WsCfg<HALF>;
+    constexpr int WIN = C::WIN, TW = C::TW, TWP = C::TWP, RB = C::RB, GT = C::GT, K = C::K, NGC = C::NGC;
+    constexpr int HBUF = C::H_BYTES / 8, PKBUF = RB * K * TW;
+    const int xB = x0 + lane;
+    uint32_t VE[NGB], VO[NGB], ringE[RB][NGB], ringO[RB][NGB];
+#pragma unroll
+    for (int j = 0; j < NGB; ++j) {
+        const int dbase = 4 * (g0 + kB * GT + j);
+        const int dmax = min(a.D, xB - HALF);
+        const uint32_t iE = (dbase + 3 > dmax ? 0x0000FFFFu : 0u) | (dbase + 1 > dmax ? 0xFFFF0000u : 0u);
+        const uint32_t iO = (dbase + 2 > dmax ? 0x0000FFFFu : 0u) | (dbase + 0 > dmax ? 0xFFFF0000u : 0u);
+        VE[j] = iE & 0x80008000u;                             // bias: never-evaluated candidates lose
+        VO[j] = iO & 0x80008000u;
+#pragma unroll
+        for (int r = 0; r < RB; ++r) { ringE[r][j] = 0; ringO[r][j] = 0; }
+    }
+    const uint32_t keybase = 4u * (uint32_t)(g0 + kB * GT);
+    const uint32_t k16 = opaque(a.k65536), mhi = opaque(a.k65536 * 0xFFFFu);
+    for (int it = 0; it < nb + 2; ++it) {
+        if (it >= 1 && it <= nb) {
+            const int batch = it - 1;
+            const uint2* Hp = Hs + (batch & 1) * HBUF + (kB * GT) * TWP + lane;
+            uint32_t* pkb = pk + (batch & 1) * PKBUF + kB * TW + lane;
+#pragma unroll
+            for (int rb = 0; rb < RB; ++rb) {
+                uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+                for (int j = 0; j < NGB; ++j) {
+                    const uint2 n = Hp[(rb * NGC + j) * TWP];
+                    VE[j] = VE[j] + n.x - ringE[(rb + RB - WIN) % RB][j];
+                    VO[j] = VO[j] + n.y - ringO[(rb + RB - WIN) % RB][j];
+                    ringE[rb][j] = n.x; ringO[rb][j] = n.y;
+                    const uint32_t kEl = key_lo(VE[j], k16, 4u * j + 3u);
+                    const uint32_t kEh = key_hi(VE[j], mhi, 4u * j + 1u);
+                    const uint32_t kOl = key_lo(VO[j], k16, 4u * j + 2u);
+                    const uint32_t kOh = key_hi(VO[j], mhi, 4u * j + 0u);
+                    best = min(best, min(kEl, kEh));
+                    best = min(best, min(kOl, kOh));
+                }
+                pkb[rb * K * TW] = best + keybase;            // rows that are not output rows are filtered by the finisher
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int HALF>
+__global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastArgs a)
+{
+    using C = WsCfg<HALF>;
+    constexpr int WIN = C::WIN, TW = C::TW, TWP = C::TWP, RB = C::RB, GT = C::GT, K = C::K, NGC = C::NGC;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint2* Hs = reinterpret_cast<uint2*>(smem);                                   // [2][RB][NGC][TWP]
+    uint32_t* Lrep = reinterpret_cast<uint32_t*>(smem + C::OFF_L);               // [2][RB][LW]
+    uint32_t* Ral = reinterpret_cast<uint32_t*>(smem + C::OFF_R);                // [2][RB][RW]
+    uint32_t* pk = reinterpret_cast<uint32_t*>(smem + C::OFF_PK);                // [2][RB][K][TW]
+    uint8_t* lut = smem + C::OFF_LUT;
+    constexpr int HBUF = C::H_BYTES / 8, LBUF = RB * C::LW, RBUF = C::R_BYTES / 4, PKBUF = RB * K * TW;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int frame = blockIdx.z / a.NC, chunk = blockIdx.z - frame * a.NC;
+    const int x0 = blockIdx.x * TW;
+    const int yb0 = a.y0 + blockIdx.y * a.BH;
+    const int yb1 = min(a.y1, yb0 + a.BH);
+    const int g0 = chunk * NGC;
+    if (yb0 >= yb1) return;
+    const int r0 = yb0 - HALF;
+    const int nb = ((yb1 - yb0) + 2 * HALF + RB - 1) / RB;
+    const int nvalid = a.W - (x0 - HALF);
+
+    for (int d = tid; d < 1040; d += C::NT) lut[d] = d <= a.D ? (uint8_t)((d * 255) / a.D) : 0;
+
+    if (warp < C::W_CONS) {
+        // ======================= producer warpgroups (warps 0..11) =======================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(C::REGS_PROD));
+        if (warp >= C::W_LOAD) {
+            // ---- tile loader: replicated L pixels and aligned R words of batch it+1 (batch 0 first) ----
+            const uint8_t* __restrict__ Lg = a.L + (long long)frame * a.frameL;
+            const uint8_t* __restrict__ Rg = a.R + (long long)frame * a.frameR;
+            const int ltid = tid - C::W_LOAD * 32;                               // 0..63
+            const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;
+            constexpr int NLQ = (RB * C::LW + 63) / 64, NRQ = (RB * C::RW + 63) / 64;
+            auto load = [&](int batch) {
+                const int rbase = r0 + batch * RB;
+                uint32_t* Ld = Lrep + (batch & 1) * LBUF;
+                uint32_t* Rd = Ral + (batch & 1) * RBUF;
+                uint32_t vl[NLQ], vr[NRQ];
+                // issue every global load of this thread before the first use: one memory round trip per batch
+#pragma unroll
+                for (int q = 0; q < NLQ; ++q) {
+                    const int idx = ltid + 64 * q;
+                    const int rb = idx / C::LW, i = idx - rb * C::LW;
+                    const int y = rbase + rb, x = x0 - HALF + i;
+                    vl[q] = 0;
+                    if (idx < RB * C::LW && (unsigned)y < (unsigned)a.H && (unsigned)x < (unsigned)a.W) vl[q] = Lg[(size_t)y * a.pitchL + x];
+                }
+#pragma unroll
+                for (int q = 0; q < NRQ; ++q) {
+                    const int idx = ltid + 64 * q;
+                    const int rb = idx / C::RW, j = idx - rb * C::RW;
+                    const int y = rbase + rb, x = xr0 + 4 * j;
+                    uint32_t v = 0;
+                    if (idx < RB * C::RW && (unsigned)y < (unsigned)a.H && x + 3 >= 0 && x < a.W) {
+                        const uint8_t* p = Rg + (size_t)y * a.pitchR;
+                        if (a.aligned && x >= 0 && x + 3 < a.W) v = *reinterpret_cast<const uint32_t*>(p + x);
+                        else {
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                if ((unsigned)(x + b) < (unsigned)a.W) v |= (uint32_t)p[x + b] << (8 * b);
+                        }
+                    }
+                    vr[q] = v;
+                }
+#pragma unroll
+                for (int q = 0; q < NLQ; ++q) { const int idx = ltid + 64 * q; if (idx < RB * C::LW) Ld[idx] = vl[q] * 0x01010101u; }
+#pragma unroll
+                for (int q = 0; q < NRQ; ++q) { const int idx = ltid + 64 * q; if (idx < RB * C::RW) Rd[idx] = vr[q]; }
+            };
+            load(0);
+            __syncthreads();
+            for (int it = 0; it < nb + 2; ++it) {
+                if (it + 1 < nb) load(it + 1);
+                __syncthreads();
+            }
+        } else {
+            // ---- walkers: warp w < 9 walks row w for groups 0..31; warp 9 walks group 32 of every row ----
+            const bool tail = warp == C::W_TAIL;
+            const int rb = tail ? lane : warp, gl = tail ? NGC - 1 : lane;
+            const bool act = !tail || lane < RB;
+            __syncthreads();
+            for (int it = 0; it < nb + 2; ++it) {
+                if (it < nb && act) {
+                    const int buf = it & 1;
+                    const uint32_t* Lr = Lrep + buf * LBUF + rb * C::LW;
+                    const uint32_t* Rr = Ral + buf * RBUF + rb * C::RW + (NGC - 1 - gl);
+                    uint2* Hout = Hs + buf * HBUF + (rb * NGC + gl) * TWP;
+                    if (nvalid >= C::NSTEP) ws_walk<HALF, false>(Lr, Rr, Hout, nvalid);
+                    else                    ws_walk<HALF, true>(Lr, Rr, Hout, nvalid);
+                }
+                __syncthreads();
+            }
+        }
+    } else {
+        // ======================= consumer warpgroups (warps 12..19) =======================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(C::REGS_CONS));
+        __syncthreads();
+        if (warp == C::W_FIN) {
+            // ---- finisher: min over the K partial keys of a pixel, LUT, store (batch it-2) ----
+            uint8_t* __restrict__ Og = a.out + (long long)frame * a.frameOut;
+            for (int it = 0; it < nb + 2; ++it) {
+                if (it >= 2) {
+                    const int batch = it - 2;
+                    const uint32_t* pkb = pk + (batch & 1) * PKBUF + lane;
+                    const int x = x0 + lane;
+#pragma unroll
+                    for (int rb = 0; rb < RB; ++rb) {
+                        const int rel = batch * RB + rb, y = r0 + rel - HALF;
+                        if (rel < 2 * HALF || y >= yb1 || x >= a.W) continue;
+                        uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int k = 0; k < K; ++k) best = min(best, pkb[(rb * K + k) * TW]);
+                        if (x < HALF) best = 0;                  // sad.go:212-218: both windows clamp, d = 0 wins
+                        if (a.NC == 1) Og[(size_t)y * a.pitchOut + x] = lut[best & 0xFFFFu];
+                        else atomicMin(a.gkey + ((size_t)frame * a.H + y) * a.W + x, ((best >> 16) << 9) | (best & 511u));
+                    }
+                }
+                __syncthreads();
+            }
+        } else {
+            // ---- consumers: vertical running sums (register ring) + argmin keys for NGB groups x 32 columns ----
+            const int kB = warp - C::W_CONS;
+            ws_consume<HALF, GT>(a, Hs, pk, kB, lane, x0, g0, r0, nb);
+        }
+    }
+}
+
+}  // namespace sadgpu

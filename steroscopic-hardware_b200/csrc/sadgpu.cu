@@ -4,6 +4,7 @@
 #include "../../include/sadgpu.h"
 #include "sad_kernels.cuh"
 #include "sad_fast.cuh"
+#include "sad_ws.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -157,6 +158,21 @@ cudaError_t launch_fast(const FastPlan& p, cudaStream_t s, bool* attr_done)
     return cudaGetLastError();
 }
 
+template <int HALF>
+cudaError_t launch_ws(const FastPlan& p, cudaStream_t s, bool* attr_done)
+{
+    using C = WsCfg<HALF>;
+    static_assert(C::SMEM <= kSmemBudget, "warp-specialised kernel does not fit shared memory");
+    auto k = sad_ws_kernel<HALF>;
+    if (!*attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return e;
+        *attr_done = true;
+    }
+    k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    return cudaGetLastError();
+}
+
 typedef cudaError_t (*fast_fn)(const FastPlan&, cudaStream_t, bool*);
 struct FastEntry { fast_fn fn; int nt, smem, rb; };
 template <int HALF, int NGC> constexpr FastEntry fast_entry()
@@ -175,10 +191,17 @@ const FastEntry kFast[8][3] = {
     {fast_entry<6, 9>(), fast_entry<6, 17>(), FastEntry{nullptr, 0, 0, 0}},
     {fast_entry<7, 9>(), fast_entry<7, 17>(), FastEntry{nullptr, 0, 0, 0}}};
 
+// slot 3 = warp-specialised kernel (sad_ws.cuh): h <= 4, 33-group chunks, 32-column strips
+const FastEntry kWs[5] = {
+    FastEntry{launch_ws<0>, WsCfg<0>::NT, WsCfg<0>::SMEM, WsCfg<0>::RB}, FastEntry{launch_ws<1>, WsCfg<1>::NT, WsCfg<1>::SMEM, WsCfg<1>::RB},
+    FastEntry{launch_ws<2>, WsCfg<2>::NT, WsCfg<2>::SMEM, WsCfg<2>::RB}, FastEntry{launch_ws<3>, WsCfg<3>::NT, WsCfg<3>::SMEM, WsCfg<3>::RB},
+    FastEntry{launch_ws<4>, WsCfg<4>::NT, WsCfg<4>::SMEM, WsCfg<4>::RB}};
+
 bool fast_supported(int B) { return B / 2 <= 7; }
+bool ws_supported(int B, int D) { return B / 2 <= 4 && (D + 4) / 4 > 17; }
 
 int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, const sadgpu_tuning* t, int sm_count,
-                   FastPlan* p, int* slot_out)
+                   FastPlan* p, int* slot_out, bool want_ws = false)
 {
     int rc = validate(w, h, B, D, y0, y1);
     if (rc) return rc;
@@ -193,12 +216,15 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
     if (t && t->groups_per_chunk > 0) {                     // tests: force smaller chunks
         slot = t->groups_per_chunk <= 9 ? 0 : t->groups_per_chunk <= 17 ? 1 : slot;
     }
-    const FastEntry& fe = kFast[half][slot];
-    p->half = half; p->ngc = kFastNgc[slot]; p->rb = fe.rb;
+    const bool ws = want_ws && ws_supported(B, D);
+    if (ws) slot = 3;
+    const FastEntry& fe = ws ? kWs[half] : kFast[half][slot];
+    const int tw = ws ? 32 : 64;
+    p->half = half; p->ngc = ws ? 33 : kFastNgc[slot]; p->rb = fe.rb;
     a.NC = ceil_div(a.NG, p->ngc);
     p->nthreads = fe.nt; p->smem = fe.smem;
     const int rows = std::max(1, y1 - y0);
-    const int nstrips = ceil_div(w, 64);
+    const int nstrips = ceil_div(w, tw);
     int nbands = 1;
     if (t && t->band_rows > 0) {
         a.BH = std::min(std::max(1, t->band_rows), rows);
@@ -246,7 +272,7 @@ struct sadgpu_ctx {
     std::mutex pool_mu;
     std::vector<std::pair<uint8_t*, size_t>> pool;
     bool attr_done[kMaxDevices][16];
-    bool fast_attr_done[kMaxDevices][8][3];
+    bool fast_attr_done[kMaxDevices][8][4];
     std::vector<size_t> dev_gkey_bytes;
     std::vector<uint32_t*> dev_gkey;       // per device scratch for sadgpu_compute_device
     std::mutex dev_mu;
@@ -289,19 +315,22 @@ int ensure_gkey(sadgpu_ctx* c, int dev_index, size_t bytes, uint32_t** out)
 int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, uint32_t* slot_gkey, cudaStream_t s)
 {
     const int variant = t ? t->kernel_variant : 0;
-    if (variant < 0 || variant > 2) return SADGPU_EINVAL;
+    if (variant < 0 || variant > 3) return SADGPU_EINVAL;
     if (variant == 2 && !fast_supported(j.B)) return SADGPU_EINVAL;
-    const bool use_fast = variant == 2 || (variant == 0 && fast_supported(j.B));
+    if (variant == 3 && !ws_supported(j.B, j.D)) return SADGPU_EINVAL;
+    const bool use_fast = variant >= 2 || (variant == 0 && fast_supported(j.B));
+    const bool want_ws = variant == 3 || variant == 0;
     int launches = 0;
     if (use_fast) {
         FastPlan p; int slot = 0;
-        int rc = make_fast_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, j.n_frames, t, c->sm_count[dev_index], &p, &slot);
+        int rc = make_fast_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, j.n_frames, t, c->sm_count[dev_index], &p, &slot, want_ws);
         if (rc) return rc;
         if (j.y1 == j.y0) return SADGPU_OK;
         FastArgs& a = p.a;
         a.L = j.dL; a.R = j.dR; a.out = j.dOut;
         a.pitchL = (int)j.pitchL; a.pitchR = (int)j.pitchR; a.pitchOut = (int)j.pitchOut;
         a.frameL = j.frameL; a.frameR = j.frameR; a.frameOut = j.frameOut;
+        a.k65536 = 65536u;
         a.aligned = ((uintptr_t)j.dR % 4 == 0 && j.pitchR % 4 == 0 && j.frameR % 4 == 0) ? 1 : 0;
         if (a.NC > 1) {
             const size_t n = (size_t)j.n_frames * j.w * j.h;
@@ -310,7 +339,8 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
             a.gkey = gk;
             sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 8192), 256, 0, s>>>(gk, n, 0xFFFFFFFFu);
         }
-        cudaError_t e = kFast[p.half][slot].fn(p, s, &c->fast_attr_done[dev_index][p.half][slot]);
+        cudaError_t e = slot == 3 ? kWs[p.half].fn(p, s, &c->fast_attr_done[dev_index][p.half][3])
+                                  : kFast[p.half][slot].fn(p, s, &c->fast_attr_done[dev_index][p.half][slot]);
         if (e != cudaSuccess) return (int)e;
         if (a.NC > 1) {
             dim3 g(ceil_div(j.w, 256), j.y1 - j.y0, j.n_frames);
@@ -617,17 +647,18 @@ int sadgpu_last_launch_count(sadgpu_ctx* c) { return c ? c->last_launches.load()
 int sadgpu_plan_describe(int w, int h, int B, int D, int y0, int y1, const sadgpu_tuning* t, char* buf, size_t buflen)
 {
     const int variant = t ? t->kernel_variant : 0;
-    if (variant == 2 || (variant == 0 && fast_supported(B))) {
+    if (variant >= 2 || (variant == 0 && fast_supported(B))) {
         FastPlan p; int slot = 0;
         const int nf = t && t->reserved[0] > 0 ? t->reserved[0] : 1;       // reserved[0]: frames per launch (describe only)
-        int rc = make_fast_plan(w, h, B, D, y0, y1, nf, t, 148, &p, &slot);
+        int rc = make_fast_plan(w, h, B, D, y0, y1, nf, t, 148, &p, &slot, variant == 3 || variant == 0);
         if (rc) return rc;
+        if (variant == 3 && slot != 3) return SADGPU_EINVAL;
         if (buf && buflen)
             snprintf(buf, buflen,
-                     "{\"variant\":\"fast\",\"half\":%d,\"NG\":%d,\"NC\":%d,\"NGc\":%d,\"TW\":64,\"RB\":%d,\"BH\":%d,"
+                     "{\"variant\":\"%s\",\"half\":%d,\"NG\":%d,\"NC\":%d,\"NGc\":%d,\"TW\":%d,\"RB\":%d,\"BH\":%d,"
                      "\"grid\":[%u,%u,%u],\"threads\":%d,\"smem\":%zu,\"launches\":%d,\"frames_per_launch\":%d}",
-                     p.half, p.a.NG, p.a.NC, p.ngc, p.rb, p.a.BH, p.grid.x, p.grid.y, p.grid.z, p.nthreads, p.smem,
-                     p.launches, nf);
+                     slot == 3 ? "warp-specialised" : "fast", p.half, p.a.NG, p.a.NC, p.ngc, slot == 3 ? 32 : 64, p.rb, p.a.BH,
+                     p.grid.x, p.grid.y, p.grid.z, p.nthreads, p.smem, p.launches, nf);
         return SADGPU_OK;
     }
     Plan p;
