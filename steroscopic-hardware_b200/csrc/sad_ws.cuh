@@ -123,6 +123,7 @@ __device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __res
                     best = min(best, min(kOl, kOh));
                 }
                 pkb[rb * K * TW] = best + keybase;            // rows that are not output rows are filtered by the finisher
+                asm volatile("" ::: "memory");   // keep ptxas from hoisting every row's loads (register ring is large)
             }
         }
         __syncthreads();
@@ -159,36 +160,50 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastAr
         // ======================= producer warpgroups (warps 0..11) =======================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(C::REGS_PROD));
         if (warp >= C::W_LOAD) {
-            // ---- tile loader: replicated L pixels and aligned R words of batch it+1 (batch 0 first) ----
+            // ---- tile loader: replicated L pixels and aligned R words.  Each thread owns fixed (row, column)
+            // slots; per batch it issues every global load of batch it+2, keeps the values in registers across
+            // the barrier and stores them (into the other tile buffer) one iteration later: the memory round
+            // trip is hidden behind a whole batch of compute. ----
             const uint8_t* __restrict__ Lg = a.L + (long long)frame * a.frameL;
             const uint8_t* __restrict__ Rg = a.R + (long long)frame * a.frameR;
             const int ltid = tid - C::W_LOAD * 32;                               // 0..63
             const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;
             constexpr int NLQ = (RB * C::LW + 63) / 64, NRQ = (RB * C::RW + 63) / 64;
-            auto load = [&](int batch) {
+            int lrow[NLQ], rrow[NRQ];                // row inside the batch, or -1 when the slot is unused / out of range in x
+            long long loff[NLQ], roff[NRQ];          // byte offset of the element inside its image row
+            int rmode[NRQ];                          // 1: aligned word, 2: partial word (edges), 0: zero
+#pragma unroll
+            for (int q = 0; q < NLQ; ++q) {
+                const int idx = ltid + 64 * q, rb = idx / C::LW, i = idx - rb * C::LW, x = x0 - HALF + i;
+                lrow[q] = (idx < RB * C::LW && (unsigned)x < (unsigned)a.W) ? rb : -1;
+                loff[q] = x;
+            }
+#pragma unroll
+            for (int q = 0; q < NRQ; ++q) {
+                const int idx = ltid + 64 * q, rb = idx / C::RW, j = idx - rb * C::RW, x = xr0 + 4 * j;
+                const bool in = idx < RB * C::RW && x + 3 >= 0 && x < a.W;
+                rrow[q] = in ? rb : -1;
+                rmode[q] = !in ? 0 : (a.aligned && x >= 0 && x + 3 < a.W) ? 1 : 2;
+                roff[q] = x;
+            }
+            uint32_t vl[NLQ], vr[NRQ];
+            auto issue = [&](int batch) {
                 const int rbase = r0 + batch * RB;
-                uint32_t* Ld = Lrep + (batch & 1) * LBUF;
-                uint32_t* Rd = Ral + (batch & 1) * RBUF;
-                uint32_t vl[NLQ], vr[NRQ];
-                // issue every global load of this thread before the first use: one memory round trip per batch
 #pragma unroll
                 for (int q = 0; q < NLQ; ++q) {
-                    const int idx = ltid + 64 * q;
-                    const int rb = idx / C::LW, i = idx - rb * C::LW;
-                    const int y = rbase + rb, x = x0 - HALF + i;
+                    const int y = rbase + lrow[q];
                     vl[q] = 0;
-                    if (idx < RB * C::LW && (unsigned)y < (unsigned)a.H && (unsigned)x < (unsigned)a.W) vl[q] = Lg[(size_t)y * a.pitchL + x];
+                    if (lrow[q] >= 0 && (unsigned)y < (unsigned)a.H) vl[q] = Lg[(size_t)y * a.pitchL + loff[q]];
                 }
 #pragma unroll
                 for (int q = 0; q < NRQ; ++q) {
-                    const int idx = ltid + 64 * q;
-                    const int rb = idx / C::RW, j = idx - rb * C::RW;
-                    const int y = rbase + rb, x = xr0 + 4 * j;
+                    const int y = rbase + rrow[q];
                     uint32_t v = 0;
-                    if (idx < RB * C::RW && (unsigned)y < (unsigned)a.H && x + 3 >= 0 && x < a.W) {
+                    if (rrow[q] >= 0 && (unsigned)y < (unsigned)a.H) {
                         const uint8_t* p = Rg + (size_t)y * a.pitchR;
-                        if (a.aligned && x >= 0 && x + 3 < a.W) v = *reinterpret_cast<const uint32_t*>(p + x);
+                        if (rmode[q] == 1) v = *reinterpret_cast<const uint32_t*>(p + roff[q]);
                         else {
+                            const int x = (int)roff[q];
 #pragma unroll
                             for (int b = 0; b < 4; ++b)
                                 if ((unsigned)(x + b) < (unsigned)a.W) v |= (uint32_t)p[x + b] << (8 * b);
@@ -196,15 +211,22 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastAr
                     }
                     vr[q] = v;
                 }
+            };
+            auto commit = [&](int batch) {
+                uint32_t* Ld = Lrep + (batch & 1) * LBUF;
+                uint32_t* Rd = Ral + (batch & 1) * RBUF;
 #pragma unroll
                 for (int q = 0; q < NLQ; ++q) { const int idx = ltid + 64 * q; if (idx < RB * C::LW) Ld[idx] = vl[q] * 0x01010101u; }
 #pragma unroll
                 for (int q = 0; q < NRQ; ++q) { const int idx = ltid + 64 * q; if (idx < RB * C::RW) Rd[idx] = vr[q]; }
             };
-            load(0);
+            issue(0); commit(0);
+            if (nb > 1) issue(1);
             __syncthreads();
             for (int it = 0; it < nb + 2; ++it) {
-                if (it + 1 < nb) load(it + 1);
+                // tiles[(it+1)&1] were last read in iteration it-1: free now
+                if (it + 1 < nb) commit(it + 1);
+                if (it + 2 < nb) issue(it + 2);
                 __syncthreads();
             }
         } else {
