@@ -61,7 +61,7 @@ typedef struct sadgpu_tuning {
     int band_rows;          /* BH: output rows per CTA band                           */
     int groups_per_chunk;   /* disparity groups (4 disparities each) per CTA chunk     */
     int kernel_variant;     /* 0 = auto, 1 = generic (any block size), 2 = register-ring fast path (block_size <= 15),
-                               3 = warp-specialised fast path (block_size <= 9, max_disparity > 64) */
+                               3 = warp-specialised fast path (block_size <= 9, max_disparity >= 68) */
     int reserved[4];        /* reserved[0]: frames per launch, used by sadgpu_plan_describe only */
 } sadgpu_tuning;
 
@@ -123,6 +123,7 @@ void *sadgpu_host_alloc(sadgpu_ctx *ctx, size_t bytes);
 void  sadgpu_host_free(sadgpu_ctx *ctx, void *p);
 
 /* Introspection used by bench.py / tests. */
+int  sadgpu_debug_read(sadgpu_ctx *ctx, int device, uint32_t *host, int n_words);   /* developer: per-role cycle counters (tuning.reserved[1] & 4) */
 int  sadgpu_last_launch_count(sadgpu_ctx *ctx);    /* kernels launched by the last compute call */
 int  sadgpu_plan_describe(int w, int h, int block_size, int max_disparity, int y0, int y1,
                           const sadgpu_tuning *tuning, char *buf, size_t buflen);

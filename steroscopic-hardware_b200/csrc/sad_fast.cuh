@@ -22,6 +22,7 @@ struct FastArgs {
     int W, H, y0, y1;
     int D, NG, NC, BH;
     int aligned;                             // R rows may be fetched with aligned 32-bit loads
+    int debug_skip;                          // developer experiments: 1 = walkers idle, 2 = consumers idle (results wrong)
     unsigned k65536;                         // = 65536, passed at run time so that v*65536+idx stays an IMAD (FMA pipe)
 };
 

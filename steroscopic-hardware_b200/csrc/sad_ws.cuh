@@ -7,11 +7,11 @@
 //   warps 0..8   walkers: warp w walks row w of the batch for 32 disparity groups (lanes = groups),
 //                horizontal running window sums -> H[buf][row][group][column] in shared memory;
 //   warp  9      walks the 33rd group (the single candidate d = 128 when D = 128), one lane per row;
-//   warps 10,11  prefetch the next batch's L/R tiles into the other tile buffer;
+//                each walker also prefetches its row of the batch after next (three tile buffers);
+//   warp  10     finisher: min over the 11 partial keys of a pixel, d*255/D LUT, store;
 //   warps 12..22 consumers: warp 12+k owns groups 3k..3k+2 for 32 columns (lanes = columns): vertical
 //                running sums with the previous 2h+1 rows in a register ring, key-min argmin, partial
 //                best -> pk; then the cross-warp min + LUT + store of the batch before.
-//   warp  23     finisher: min over the 11 partial keys of a pixel, d*255/D LUT, store.
 // Producers work on batch i while consumers work on batch i-1 (H and tiles are double-buffered).
 #pragma once
 #include <cstdint>
@@ -29,9 +29,9 @@ template <int HALF> struct WsCfg {
     static constexpr int NGC = 33, GT = 3, K = 11;     // groups per chunk, groups per consumer thread, consumer warps
     // warp roles (6 warpgroups of 4 warps): producers = warps 0..11, consumers = warps 12..23
     static constexpr int W_TAIL = RB;                  // warp 9: 33rd group, one lane per row
-    static constexpr int W_LOAD = 10;                  // warps 10,11: tile prefetch
-    static constexpr int W_CONS = 12;                  // warps 12..22: consumer k = warp-12
-    static constexpr int W_FIN = W_CONS + K;           // warp 23: cross-warp min + LUT + store
+    static constexpr int W_FIN = 10;                   // warp 10: cross-warp min + LUT + store (warp 11 idles)
+    static constexpr int NTILE = 3;                    // tile buffers: walkers prefetch two batches ahead
+    static constexpr int W_CONS = 12;                  // warps 12..22: consumer k = warp-12 (warp 23 idles)
     static constexpr int NT = 768;
     static constexpr int REGS_LAUNCH = 80, REGS_PROD = 56, REGS_CONS = 104;   // setmaxnreg moves registers inside the CTA's launch allocation
     static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
@@ -42,13 +42,13 @@ template <int HALF> struct WsCfg {
     static constexpr int R_BYTES = ((RB * RW * 4 + 15) / 16) * 16;
     static constexpr int PK_BYTES = RB * K * TW * 4;
     static constexpr int OFF_L = 2 * H_BYTES;
-    static constexpr int OFF_R = OFF_L + 2 * L_BYTES;
-    static constexpr int OFF_PK = OFF_R + 2 * R_BYTES;
+    static constexpr int OFF_R = OFF_L + NTILE * L_BYTES;
+    static constexpr int OFF_PK = OFF_R + NTILE * R_BYTES;
     static constexpr int OFF_LUT = OFF_PK + 2 * PK_BYTES;
     static constexpr int SMEM = OFF_LUT + 1040;
     static_assert(WIN <= RB, "register ring shorter than the window");
     static_assert(NT * REGS_LAUNCH <= 65536 && 384 * REGS_PROD + 384 * REGS_CONS <= NT * REGS_LAUNCH, "register budget");
-    static_assert(GT * K == NGC && W_FIN == 23, "warp roles");
+    static_assert(GT * K == NGC && W_CONS + K <= 24, "warp roles");
 };
 
 // One (row, group) walk: TW outputs, NSTEP steps, fully unrolled (see fast_walk in sad_fast.cuh).
@@ -101,8 +101,12 @@ __device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __res
     }
     const uint32_t keybase = 4u * (uint32_t)(g0 + kB * GT);
     const uint32_t k16 = opaque(a.k65536), mhi = opaque(a.k65536 * 0xFFFFu);
+    long long tw = 0, tb = 0, cprev = 0;
     for (int it = 0; it < nb + 2; ++it) {
-        if (it >= 1 && it <= nb) {
+        if (a.debug_skip & 4) { const volatile uint32_t* vq = pk; tw += (long long)(vq[0] & 0u); }       // forces the deferred barrier wait to complete
+        const long long c0 = clock64();
+        if ((a.debug_skip & 4) && it > 0) tb += c0 - cprev;
+        if (it >= 1 && it <= nb && (a.debug_skip & 3) != 2) {
             const int batch = it - 1;
             const uint2* Hp = Hs + (batch & 1) * HBUF + (kB * GT) * TWP + lane;
             uint32_t* pkb = pk + (batch & 1) * PKBUF + kB * TW + lane;
@@ -123,10 +127,15 @@ __device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __res
                     best = min(best, min(kOl, kOh));
                 }
                 pkb[rb * K * TW] = best + keybase;            // rows that are not output rows are filtered by the finisher
-                asm volatile("" ::: "memory");   // keep ptxas from hoisting every row's loads (register ring is large)
             }
         }
+        const long long c1 = clock64();
         __syncthreads();
+        if (a.debug_skip & 4) { tw += c1 - c0; cprev = c1; }
+    }
+    if ((a.debug_skip & 4) && lane == 0 && blockIdx.x == 7 && blockIdx.y == 0 && blockIdx.z == 0) {
+        const int warp = kB + C::W_CONS;
+        a.gkey[warp * 4 + 0] = (uint32_t)tw; a.gkey[warp * 4 + 1] = 0; a.gkey[warp * 4 + 2] = (uint32_t)tb; a.gkey[warp * 4 + 3] = nb;
     }
 }
 
@@ -159,101 +168,10 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastAr
     if (warp < C::W_CONS) {
         // ======================= producer warpgroups (warps 0..11) =======================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(C::REGS_PROD));
-        if (warp >= C::W_LOAD) {
-            // ---- tile loader: replicated L pixels and aligned R words.  Each thread owns fixed (row, column)
-            // slots; per batch it issues every global load of batch it+2, keeps the values in registers across
-            // the barrier and stores them (into the other tile buffer) one iteration later: the memory round
-            // trip is hidden behind a whole batch of compute. ----
-            const uint8_t* __restrict__ Lg = a.L + (long long)frame * a.frameL;
-            const uint8_t* __restrict__ Rg = a.R + (long long)frame * a.frameR;
-            const int ltid = tid - C::W_LOAD * 32;                               // 0..63
-            const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;
-            constexpr int NLQ = (RB * C::LW + 63) / 64, NRQ = (RB * C::RW + 63) / 64;
-            int lrow[NLQ], rrow[NRQ];                // row inside the batch, or -1 when the slot is unused / out of range in x
-            long long loff[NLQ], roff[NRQ];          // byte offset of the element inside its image row
-            int rmode[NRQ];                          // 1: aligned word, 2: partial word (edges), 0: zero
-#pragma unroll
-            for (int q = 0; q < NLQ; ++q) {
-                const int idx = ltid + 64 * q, rb = idx / C::LW, i = idx - rb * C::LW, x = x0 - HALF + i;
-                lrow[q] = (idx < RB * C::LW && (unsigned)x < (unsigned)a.W) ? rb : -1;
-                loff[q] = x;
-            }
-#pragma unroll
-            for (int q = 0; q < NRQ; ++q) {
-                const int idx = ltid + 64 * q, rb = idx / C::RW, j = idx - rb * C::RW, x = xr0 + 4 * j;
-                const bool in = idx < RB * C::RW && x + 3 >= 0 && x < a.W;
-                rrow[q] = in ? rb : -1;
-                rmode[q] = !in ? 0 : (a.aligned && x >= 0 && x + 3 < a.W) ? 1 : 2;
-                roff[q] = x;
-            }
-            uint32_t vl[NLQ], vr[NRQ];
-            auto issue = [&](int batch) {
-                const int rbase = r0 + batch * RB;
-#pragma unroll
-                for (int q = 0; q < NLQ; ++q) {
-                    const int y = rbase + lrow[q];
-                    vl[q] = 0;
-                    if (lrow[q] >= 0 && (unsigned)y < (unsigned)a.H) vl[q] = Lg[(size_t)y * a.pitchL + loff[q]];
-                }
-#pragma unroll
-                for (int q = 0; q < NRQ; ++q) {
-                    const int y = rbase + rrow[q];
-                    uint32_t v = 0;
-                    if (rrow[q] >= 0 && (unsigned)y < (unsigned)a.H) {
-                        const uint8_t* p = Rg + (size_t)y * a.pitchR;
-                        if (rmode[q] == 1) v = *reinterpret_cast<const uint32_t*>(p + roff[q]);
-                        else {
-                            const int x = (int)roff[q];
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                                if ((unsigned)(x + b) < (unsigned)a.W) v |= (uint32_t)p[x + b] << (8 * b);
-                        }
-                    }
-                    vr[q] = v;
-                }
-            };
-            auto commit = [&](int batch) {
-                uint32_t* Ld = Lrep + (batch & 1) * LBUF;
-                uint32_t* Rd = Ral + (batch & 1) * RBUF;
-#pragma unroll
-                for (int q = 0; q < NLQ; ++q) { const int idx = ltid + 64 * q; if (idx < RB * C::LW) Ld[idx] = vl[q] * 0x01010101u; }
-#pragma unroll
-                for (int q = 0; q < NRQ; ++q) { const int idx = ltid + 64 * q; if (idx < RB * C::RW) Rd[idx] = vr[q]; }
-            };
-            issue(0); commit(0);
-            if (nb > 1) issue(1);
-            __syncthreads();
-            for (int it = 0; it < nb + 2; ++it) {
-                // tiles[(it+1)&1] were last read in iteration it-1: free now
-                if (it + 1 < nb) commit(it + 1);
-                if (it + 2 < nb) issue(it + 2);
-                __syncthreads();
-            }
-        } else {
-            // ---- walkers: warp w < 9 walks row w for groups 0..31; warp 9 walks group 32 of every row ----
-            const bool tail = warp == C::W_TAIL;
-            const int rb = tail ? lane : warp, gl = tail ? NGC - 1 : lane;
-            const bool act = !tail || lane < RB;
-            __syncthreads();
-            for (int it = 0; it < nb + 2; ++it) {
-                if (it < nb && act) {
-                    const int buf = it & 1;
-                    const uint32_t* Lr = Lrep + buf * LBUF + rb * C::LW;
-                    const uint32_t* Rr = Ral + buf * RBUF + rb * C::RW + (NGC - 1 - gl);
-                    uint2* Hout = Hs + buf * HBUF + (rb * NGC + gl) * TWP;
-                    if (nvalid >= C::NSTEP) ws_walk<HALF, false>(Lr, Rr, Hout, nvalid);
-                    else                    ws_walk<HALF, true>(Lr, Rr, Hout, nvalid);
-                }
-                __syncthreads();
-            }
-        }
-    } else {
-        // ======================= consumer warpgroups (warps 12..19) =======================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(C::REGS_CONS));
-        __syncthreads();
         if (warp == C::W_FIN) {
             // ---- finisher: min over the K partial keys of a pixel, LUT, store (batch it-2) ----
             uint8_t* __restrict__ Og = a.out + (long long)frame * a.frameOut;
+            __syncthreads();
             for (int it = 0; it < nb + 2; ++it) {
                 if (it >= 2) {
                     const int batch = it - 2;
@@ -273,10 +191,101 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastAr
                 }
                 __syncthreads();
             }
+        } else if (warp > C::W_FIN) {
+            __syncthreads();
+            for (int it = 0; it < nb + 2; ++it) __syncthreads();       // spare warp of the producer register class
         } else {
-            // ---- consumers: vertical running sums (register ring) + argmin keys for NGB groups x 32 columns ----
-            const int kB = warp - C::W_CONS;
+            // ---- walkers: warp w < 9 walks row w for groups 0..31 and prefetches row w of the batch after next
+            //      (L pixels replicated, R as aligned words) into the third tile buffer; warp 9 walks group 32
+            //      of every row (one lane per row). ----
+            const bool tail = warp == C::W_TAIL;
+            const int rb = tail ? lane : warp, gl = tail ? NGC - 1 : lane;
+            const bool act = !tail || lane < RB;
+            const uint8_t* __restrict__ Lg = a.L + (long long)frame * a.frameL;
+            const uint8_t* __restrict__ Rg = a.R + (long long)frame * a.frameR;
+            const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;
+            constexpr int NLQ = (C::LW + 31) / 32, NRQ = (C::RW + 31) / 32;
+            int lx[NLQ], rx[NRQ], rmode[NRQ];            // column of each slot of this lane; -1 / mode 0 = zero
+#pragma unroll
+            for (int q = 0; q < NLQ; ++q) {
+                const int i = lane + 32 * q, x = x0 - HALF + i;
+                lx[q] = (i < C::LW && (unsigned)x < (unsigned)a.W) ? x : -1;
+            }
+#pragma unroll
+            for (int q = 0; q < NRQ; ++q) {
+                const int j = lane + 32 * q, x = xr0 + 4 * j;
+                const bool in = j < C::RW && x + 3 >= 0 && x < a.W;
+                rx[q] = x;
+                rmode[q] = !in ? 0 : (a.aligned && x >= 0 && x + 3 < a.W) ? 1 : 2;
+            }
+            uint32_t vl[NLQ], vr[NRQ];
+            auto issue = [&](int batch) {               // global loads of row rb of `batch` (warp-uniform row test)
+                const int y = r0 + batch * RB + rb;
+                const bool yin = (unsigned)y < (unsigned)a.H;
+                const uint8_t* pl = Lg + (size_t)(yin ? y : 0) * a.pitchL;
+                const uint8_t* pr = Rg + (size_t)(yin ? y : 0) * a.pitchR;
+#pragma unroll
+                for (int q = 0; q < NLQ; ++q) { vl[q] = 0; if (yin && lx[q] >= 0) vl[q] = pl[lx[q]]; }
+#pragma unroll
+                for (int q = 0; q < NRQ; ++q) {
+                    uint32_t v = 0;
+                    if (yin && rmode[q] == 1) v = *reinterpret_cast<const uint32_t*>(pr + rx[q]);
+                    else if (yin && rmode[q] == 2) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if ((unsigned)(rx[q] + b) < (unsigned)a.W) v |= (uint32_t)pr[rx[q] + b] << (8 * b);
+                    }
+                    vr[q] = v;
+                }
+            };
+            auto commit = [&](int batch) {
+                uint32_t* Ld = Lrep + (batch % C::NTILE) * LBUF + rb * C::LW;
+                uint32_t* Rd = Ral + (batch % C::NTILE) * RBUF + rb * C::RW;
+#pragma unroll
+                for (int q = 0; q < NLQ; ++q) { const int i = lane + 32 * q; if (i < C::LW) Ld[i] = vl[q] * 0x01010101u; }
+#pragma unroll
+                for (int q = 0; q < NRQ; ++q) { const int j = lane + 32 * q; if (j < C::RW) Rd[j] = vr[q]; }
+            };
+            if (!tail) {
+                issue(0); commit(0);
+                if (nb > 1) { issue(1); commit(1); }
+            }
+            __syncthreads();
+            long long tw = 0, tc = 0, tb = 0, cprev = 0;
+            for (int it = 0; it < nb + 2; ++it) {
+                if (a.debug_skip & 4) { volatile uint8_t* vq = lut; tw += (long long)(vq[0] & 0) ; }   // forces the deferred barrier wait to complete
+                const long long c0 = clock64();
+                if ((a.debug_skip & 4) && it > 0) tb += c0 - cprev;
+                const bool pre = !tail && it + 2 < nb;
+                if (pre) issue(it + 2);
+                if (it < nb && act && (a.debug_skip & 3) != 1) {
+                    const int buf = it & 1, tb = it % C::NTILE;
+                    const uint32_t* Lr = Lrep + tb * LBUF + rb * C::LW;
+                    const uint32_t* Rr = Ral + tb * RBUF + rb * C::RW + (NGC - 1 - gl);
+                    uint2* Hout = Hs + buf * HBUF + (rb * NGC + gl) * TWP;
+                    if (nvalid >= C::NSTEP) ws_walk<HALF, false>(Lr, Rr, Hout, nvalid);
+                    else                    ws_walk<HALF, true>(Lr, Rr, Hout, nvalid);
+                }
+                const long long c1 = clock64();
+                if (pre) commit(it + 2);               // tile buffer (it+2)%3 was last read in iteration it-1
+                const long long c2 = clock64();
+                __syncthreads();
+                if (a.debug_skip & 4) { tw += c1 - c0; tc += c2 - c1; cprev = c2; }
+            }
+            if ((a.debug_skip & 4) && lane == 0 && blockIdx.x == 7 && blockIdx.y == 0 && blockIdx.z == 0) {
+                a.gkey[warp * 4 + 0] = (uint32_t)tw; a.gkey[warp * 4 + 1] = (uint32_t)tc; a.gkey[warp * 4 + 2] = (uint32_t)tb; a.gkey[warp * 4 + 3] = nb;
+            }
+        }
+    } else {
+        // ======================= consumer warpgroups (warps 12..23) =======================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(C::REGS_CONS));
+        __syncthreads();
+        const int kB = warp - C::W_CONS;
+        if (kB < K) {
+            // ---- consumers: vertical running sums (register ring) + argmin keys for GT groups x 32 columns ----
             ws_consume<HALF, GT>(a, Hs, pk, kB, lane, x0, g0, r0, nb);
+        } else {
+            for (int it = 0; it < nb + 2; ++it) __syncthreads();       // spare warp of the consumer register class
         }
     }
 }

@@ -331,7 +331,9 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
         a.pitchL = (int)j.pitchL; a.pitchR = (int)j.pitchR; a.pitchOut = (int)j.pitchOut;
         a.frameL = j.frameL; a.frameR = j.frameR; a.frameOut = j.frameOut;
         a.k65536 = 65536u;
+        a.debug_skip = t ? t->reserved[1] : 0;
         a.aligned = ((uintptr_t)j.dR % 4 == 0 && j.pitchR % 4 == 0 && j.frameR % 4 == 0) ? 1 : 0;
+        if (a.debug_skip & 4) { uint32_t* gk = nullptr; rc = ensure_gkey(c, dev_index, 4096, &gk); if (rc) return rc; a.gkey = gk; }
         if (a.NC > 1) {
             const size_t n = (size_t)j.n_frames * j.w * j.h;
             uint32_t* gk = slot_gkey;
@@ -640,6 +642,16 @@ void sadgpu_host_free(sadgpu_ctx* c, void* p)
     std::lock_guard<std::mutex> g(c->pool_mu);
     for (size_t i = 0; i < c->pool.size(); ++i)
         if (c->pool[i].first == p) { cudaFreeHost(p); c->pool.erase(c->pool.begin() + i); return; }
+}
+
+int sadgpu_debug_read(sadgpu_ctx* c, int device, uint32_t* host, int n_words)
+{
+    if (!c || !host || device < 0 || device >= (int)c->devices.size() || n_words < 0) return SADGPU_EINVAL;
+    if (!c->dev_gkey[device] || c->dev_gkey_bytes[device] < (size_t)n_words * 4) return SADGPU_ERANGE;
+    cudaError_t e = cudaSetDevice(c->devices[device]);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(host, c->dev_gkey[device], (size_t)n_words * 4, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? SADGPU_OK : (int)e;
 }
 
 int sadgpu_last_launch_count(sadgpu_ctx* c) { return c ? c->last_launches.load() : 0; }

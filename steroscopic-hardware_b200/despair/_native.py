@@ -36,6 +36,7 @@ EXPORTS = {
                                             c_size_t, c_void_p, ctypes.POINTER(Tuning)]),
     "sadgpu_host_alloc": (c_void_p, [c_void_p, c_size_t]),
     "sadgpu_host_free": (None, [c_void_p, c_void_p]),
+    "sadgpu_debug_read": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_uint32), c_int]),
     "sadgpu_last_launch_count": (c_int, [c_void_p]),
     "sadgpu_plan_describe": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(Tuning),
                                      ctypes.c_char_p, c_size_t]),

@@ -38,7 +38,7 @@ def main():
         if i % 3 == 1: tun = dict(rows_per_batch=int(rng.integers(1, 9)), band_rows=int(rng.integers(1, 40)), groups_per_chunk=int(rng.integers(1, 21)))
         if B <= 15 and i % 2 == 0:
             tun = dict(tun or {}); tun['kernel_variant'] = 2
-        if B <= 9 and D > 64 and i % 4 == 1:
+        if B <= 9 and D >= 68 and i % 4 == 1:
             tun = dict(tun or {}); tun['kernel_variant'] = 3
         got = dev_run(ctx, L, R, B, D, tun)
         ncase += 1
