@@ -13,6 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libsadgpu.so")
+HOST_LIB = os.path.join(HERE, "libdespair_host.so")
+HOST = os.path.join(HERE, "host")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -35,7 +37,15 @@ def sources():
 def build_all(force=False, verbose=False):
     srcs = sources()
     if force or _stale(LIB, srcs):
-        cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "sadgpu.cu")]
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-diag-suppress", "39", "-o", LIB, os.path.join(CSRC, "sadgpu.cu")]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    # C++ mirror of pkg/despair (host threads over the C ABI); links against libsadgpu.so in the same directory
+    hsrcs = [os.path.join(HOST, f) for f in sorted(os.listdir(HOST))] + [os.path.join(ROOT, "include", "sadgpu.h"), LIB]
+    if force or _stale(HOST_LIB, hsrcs):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", HOST_LIB, os.path.join(HOST, "despair.cpp"),
+               "-L" + HERE, "-lsadgpu", "-Wl,-rpath,$ORIGIN"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

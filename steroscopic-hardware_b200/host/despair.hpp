@@ -1,0 +1,115 @@
+// despair.hpp — C++ host-side mirror of the reference Go package pkg/despair over the sadgpu C ABI.
+//
+// The reference's host language (Go 1.24) is not available in the build image, so the layer that a
+// `//go:build cuda` file would provide is written here in C++ with the same names,
+// argument meaning and semantics, one to one:
+//
+//   Parameters / SetDefaultParams / DefaultParams      pkg/despair/params.go:8-37
+//   InputChunk / OutputChunk                           pkg/despair/sad.go:12-21
+//   SetupConcurrentSAD(numWorkers)                     pkg/despair/sad.go:29-113
+//   RunSad(left, right, blockSize, maxDisparity)       pkg/despair/sad.go:119-169
+//   AssembleDisparityMap(out, dimensions, chunks)      pkg/despair/sad.go:172-202
+//
+// Chan<T> is a bounded MPMC queue with Go channel semantics (blocking send/recv, close drains).
+// The workers do not compute anything themselves: every chunk ends in sadgpu_compute (CUDA); there
+// is no CPU path.  Deviations from the reference are the documented ones: all
+// chunks are written by AssembleDisparityMap (the dropped-last-chunk bug of sad.go:179-184 is
+// available behind `faithful_drop` for comparison tests only), parameters are read once per chunk
+// exactly as in sad.go:51-53, invalid parameters surface as std::runtime_error where Go panics.
+#pragma once
+#include <condition_variable>
+#include <cstdint>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <vector>
+
+struct sadgpu_ctx;
+
+namespace despair {
+
+struct Rectangle {                      // image.Rectangle
+    int MinX = 0, MinY = 0, MaxX = 0, MaxY = 0;
+    int Dx() const { return MaxX - MinX; }
+    int Dy() const { return MaxY - MinY; }
+};
+inline Rectangle Rect(int x0, int y0, int x1, int y1) { return Rectangle{x0, y0, x1, y1}; }
+
+struct Gray {                           // image.Gray: Pix, Stride, Rect (Rect.Min must be (0,0), as sad.go:228 assumes)
+    std::vector<uint8_t> Pix;
+    int Stride = 0;
+    Rectangle Rect_;
+};
+Gray NewGray(Rectangle r);
+
+struct Parameters {                     // pkg/despair/params.go:34-37
+    int BlockSize;
+    int MaxDisparity;
+};
+void SetDefaultParams(Parameters p);    // params.go:21-25
+Parameters DefaultParams();             // params.go:28-30 (initial value {16, 64}, params.go:13-18)
+
+struct InputChunk {                     // sad.go:12-15
+    const Gray* Left = nullptr;
+    const Gray* Right = nullptr;
+    Rectangle Region;
+};
+struct OutputChunk {                    // sad.go:18-21
+    std::vector<uint8_t> DisparityData;
+    Rectangle Region;
+};
+
+template <class T> class Chan {         // buffered Go channel
+public:
+    explicit Chan(size_t cap) : cap_(cap ? cap : 1) {}
+    void Send(T v) {
+        std::unique_lock<std::mutex> l(m_);
+        not_full_.wait(l, [&] { return q_.size() < cap_ || closed_; });
+        if (closed_) throw std::runtime_error("send on closed channel");
+        q_.push_back(std::move(v));
+        not_empty_.notify_one();
+    }
+    bool Recv(T& out) {                 // false once the channel is closed and drained (Go: v, ok := <-ch)
+        std::unique_lock<std::mutex> l(m_);
+        not_empty_.wait(l, [&] { return !q_.empty() || closed_; });
+        if (q_.empty()) return false;
+        out = std::move(q_.front());
+        q_.pop_front();
+        not_full_.notify_one();
+        return true;
+    }
+    void Close() {
+        std::lock_guard<std::mutex> l(m_);
+        closed_ = true;
+        not_empty_.notify_all();
+        not_full_.notify_all();
+    }
+    size_t Cap() const { return cap_; }
+private:
+    std::mutex m_;
+    std::condition_variable not_empty_, not_full_;
+    std::deque<T> q_;
+    size_t cap_;
+    bool closed_ = false;
+};
+
+struct Pipeline {                       // the (chan<- InputChunk, <-chan OutputChunk) pair of SetupConcurrentSAD
+    std::shared_ptr<Chan<InputChunk>> In;
+    std::shared_ptr<Chan<OutputChunk>> Out;
+};
+
+// numWorkers <= 0 => hardware_concurrency*4 (sad.go:32-34); channels buffered 2*numWorkers (:36-37).
+// Worker w owns CUDA stream slot w of a shared sadgpu context (created on first use, sized max_w x max_h).
+Pipeline SetupConcurrentSAD(int numWorkers);
+Gray RunSad(const Gray& left, const Gray& right, int blockSize, int maxDisparity);
+Gray AssembleDisparityMap(Chan<OutputChunk>& outputChan, Rectangle dimensions, int chunks, bool faithful_drop = false);
+
+// Tile planner of RunSad (sad.go:128-153), exposed for tests.
+std::vector<Rectangle> RunSadChunks(Rectangle dims, int numCPU);
+
+// Configuration of the backing context (additive; the reference has no equivalent).
+void ConfigureBackend(int max_w, int max_h, int n_streams);
+void ShutdownBackend();
+
+}  // namespace despair

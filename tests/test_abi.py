@@ -41,11 +41,19 @@ def test_plans_cover_the_parameter_surface(native):
     import despair
     for B in range(1, 32):
         for D in (1, 16, 64, 128, 255, 256):
-            p = despair.plan_describe(1920, 1080, B, D)
-            assert p["half"] == B // 2 and p["smem"] <= 232448 and p["NC"] * p["NGc"] >= p["NG"]
-            assert p["TW"] == p["NSTEP"] - 2 * (B // 2)
-    p = despair.plan_describe(1920, 1080, 9, 128)
-    assert p["grid"][0] * p["TW"] >= 1920
+            for variant in (0, 1):
+                p = despair.plan_describe(1920, 1080, B, D, tuning=dict(kernel_variant=variant))
+                assert p["half"] == B // 2 and p["smem"] <= 232448 and p["NC"] * p["NGc"] >= p["NG"]
+                assert p["grid"][0] * p["TW"] >= 1920
+                if p["variant"] == "generic":
+                    assert p["TW"] == p["NSTEP"] - 2 * (B // 2)
+                else:
+                    assert B <= 15
+    assert despair.plan_describe(1920, 1080, 9, 128)["variant"] == "warp-specialised"
+    assert despair.plan_describe(1920, 1080, 15, 256)["variant"] == "fast"
+    assert despair.plan_describe(1920, 1080, 31, 256)["variant"] == "generic"
+    with pytest.raises(despair.SadGpuError):
+        despair.plan_describe(1920, 1080, 31, 256, tuning=dict(kernel_variant=2))      # fast path needs block_size <= 15
 
 
 def test_plan_rejects_bad_parameters(native):
