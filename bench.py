@@ -213,7 +213,7 @@ def main():
         parity = bool(np.array_equal(dO[0].cpu().numpy()[520:536], exp))
 
     # ---- e2e: C ABI with host buffers (pinned pool), submit/wait pipelined over n_streams ----
-    pin = [(ctx.host_array((H, W)), ctx.host_array((H, W))) for _ in range(nuniq)]
+    pin = [ctx.host_pair(H, W) for _ in range(nuniq)]          # left/right back to back: one H2D DMA per frame pair
     for k in range(nuniq):
         pin[k][0][:] = gen[k][0]; pin[k][1][:] = gen[k][1]
     outs = [ctx.host_array((H, W)) for _ in range(n_streams)]

@@ -253,7 +253,7 @@ struct Slot {
     uint8_t *hL = nullptr, *hR = nullptr, *hOut = nullptr;     // pinned staging
     uint8_t *dL = nullptr, *dR = nullptr, *dOut = nullptr;     // device, pitched
     uint32_t* gkey = nullptr;
-    size_t pitch = 0;
+    size_t pitch = 0;                                          // pitch of the frame in flight = round_up(w, 4): contiguous copies when the host stride matches
     std::mutex mu;
     bool busy = false;
     uint64_t seq = 0;
@@ -401,8 +401,12 @@ int upload(sadgpu_ctx* c, Slot* s, const uint8_t* src, int stride, uint8_t* pinn
         else for (int y = 0; y < n; ++y) memcpy(st + (size_t)y * s->pitch, from + (size_t)y * stride, (size_t)w);
         from = st; from_pitch = s->pitch;
     }
-    cudaError_t e = cudaMemcpy2DAsync(dev + (size_t)ys * s->pitch, s->pitch, from, from_pitch, (size_t)w, (size_t)n,
-                                      cudaMemcpyHostToDevice, s->st);
+    cudaError_t e;
+    if (from_pitch == s->pitch && s->pitch == (size_t)w)        // one contiguous DMA
+        e = cudaMemcpyAsync(dev + (size_t)ys * s->pitch, from, (size_t)n * w, cudaMemcpyHostToDevice, s->st);
+    else
+        e = cudaMemcpy2DAsync(dev + (size_t)ys * s->pitch, s->pitch, from, from_pitch, (size_t)w, (size_t)n,
+                              cudaMemcpyHostToDevice, s->st);
     return e == cudaSuccess ? SADGPU_OK : (int)e;
 }
 
@@ -415,16 +419,33 @@ int submit_locked(sadgpu_ctx* c, Slot* s, const uint8_t* l, int ls, const uint8_
     if (rc) return rc;
     const int half = B / 2;
     const int ys = std::max(0, y0 - half), ye = std::min(h, y1 + half);
-    if ((rc = upload(c, s, l, ls, s->hL, s->dL, w, ys, ye))) return rc;
-    if ((rc = upload(c, s, r, rs, s->hR, s->dR, w, ys, ye))) return rc;
+    s->pitch = (size_t)round_up(w, 4);
+    s->dR = s->dL + s->pitch * (size_t)h;                      // right image directly behind the left one
+    s->hR = s->hL + s->pitch * (size_t)h;
+    const size_t img = s->pitch * (size_t)h;
+    const bool whole = ys == 0 && ye == h && s->pitch == (size_t)w && ls == w && rs == w;
+    if (whole && r == l + img && in_pool(c, l, 2 * img)) {     // caller's pinned pair is contiguous: one DMA, zero staging
+        cudaError_t e1 = cudaMemcpyAsync(s->dL, l, 2 * img, cudaMemcpyHostToDevice, s->st);
+        if (e1 != cudaSuccess) return (int)e1;
+    } else if (whole && !in_pool(c, l, img) && !in_pool(c, r, img)) {   // pageable pair: stage both, one DMA
+        memcpy(s->hL, l, img); memcpy(s->hR, r, img);
+        cudaError_t e1 = cudaMemcpyAsync(s->dL, s->hL, 2 * img, cudaMemcpyHostToDevice, s->st);
+        if (e1 != cudaSuccess) return (int)e1;
+    } else {
+        if ((rc = upload(c, s, l, ls, s->hL, s->dL, w, ys, ye))) return rc;
+        if ((rc = upload(c, s, r, rs, s->hR, s->dR, w, ys, ye))) return rc;
+    }
     if (y1 > y0) {
         Job j{s->dL, s->pitch, 0, s->dR, s->pitch, 0, s->dOut, s->pitch, 0, 1, w, h, B, D, y0, y1};
         if ((rc = run_job(c, s->dev_index, j, nullptr, s->gkey, s->st))) return rc;
         s->out_direct = direct_out != nullptr;
         uint8_t* dst = direct_out ? direct_out + (size_t)y0 * direct_stride : s->hOut + (size_t)y0 * s->pitch;
         const size_t dpitch = direct_out ? (size_t)direct_stride : s->pitch;
-        e = cudaMemcpy2DAsync(dst, dpitch, s->dOut + (size_t)y0 * s->pitch, s->pitch, (size_t)w, (size_t)(y1 - y0),
-                              cudaMemcpyDeviceToHost, s->st);
+        if (dpitch == s->pitch && s->pitch == (size_t)w)
+            e = cudaMemcpyAsync(dst, s->dOut + (size_t)y0 * s->pitch, (size_t)(y1 - y0) * w, cudaMemcpyDeviceToHost, s->st);
+        else
+            e = cudaMemcpy2DAsync(dst, dpitch, s->dOut + (size_t)y0 * s->pitch, s->pitch, (size_t)w, (size_t)(y1 - y0),
+                                  cudaMemcpyDeviceToHost, s->st);
         if (e != cudaSuccess) return (int)e;
     }
     e = cudaEventRecord(s->done, s->st);
@@ -454,8 +475,8 @@ void free_slot(Slot* s)
     cudaSetDevice(s->device);
     if (s->st) { cudaStreamSynchronize(s->st); cudaStreamDestroy(s->st); }
     if (s->done) cudaEventDestroy(s->done);
-    cudaFreeHost(s->hL); cudaFreeHost(s->hR); cudaFreeHost(s->hOut);
-    cudaFree(s->dL); cudaFree(s->dR); cudaFree(s->dOut); cudaFree(s->gkey);
+    cudaFreeHost(s->hL); cudaFreeHost(s->hOut);
+    cudaFree(s->dL); cudaFree(s->dOut); cudaFree(s->gkey);
     delete s;
 }
 
@@ -501,15 +522,16 @@ int sadgpu_create(const int* devices, int n_devices, int max_w, int max_h, int n
         Slot* s = new (std::nothrow) Slot();
         if (!s) { sadgpu_destroy(c); return SADGPU_ENOMEM; }
         c->slots.push_back(s);
-        s->dev_index = i % n_devices; s->device = c->devices[s->dev_index]; s->pitch = pitch;
+        s->dev_index = i % n_devices; s->device = c->devices[s->dev_index]; s->pitch = pitch;   // re-set per frame
         e = cudaSetDevice(s->device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hL, img, cudaHostAllocPortable);
-        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hR, img, cudaHostAllocPortable);
+        // left and right live back to back (pinned and device) so that a whole frame pair is ONE DMA
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hL, 2 * img, cudaHostAllocPortable);
+        if (e == cudaSuccess) s->hR = s->hL + img;
         if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hOut, img, cudaHostAllocPortable);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->dL, img);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->dR, img);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->dL, 2 * img);
+        if (e == cudaSuccess) s->dR = s->dL + img;
         if (e == cudaSuccess) e = cudaMalloc((void**)&s->dOut, img);
         if (e == cudaSuccess) e = cudaMalloc((void**)&s->gkey, (size_t)max_w * max_h * sizeof(uint32_t));
         if (e != cudaSuccess) { sadgpu_destroy(c); return (int)e; }

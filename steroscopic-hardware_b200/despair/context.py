@@ -111,6 +111,11 @@ class Context:
         a = np.frombuffer(buf, np.uint8).reshape(shape)
         return a
 
+    def host_pair(self, h, w):
+        """left/right frames back to back in one pinned allocation: uploaded with a single DMA."""
+        a = self.host_array((2, h, w))
+        return a[0], a[1]
+
     def last_launch_count(self):
         return self._L.sadgpu_last_launch_count(self._h)
 
