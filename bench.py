@@ -30,7 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "steroscopic-hardware_b200"))
 import numpy as np
 
 W, H, B, D = 1920, 1080, 9, 128
-FRAMES = 64                       # frame pairs per step per GPU: 265 MB of input > L2
+FRAMES = 256                      # frame pairs per step per GPU: 1.06 GB of input >> the 126 MB L2
 OPS_PER_EVAL = 6                  # 1 abs-diff + 2 + 2 running-sum add/sub + 1 compare-select
 METRIC = "disparity_evals_per_sec_1080p_D128_B9"
 UNIT = "Mpix*D/s"
@@ -53,8 +53,10 @@ def mpixd(frames, seconds):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md).  Started before the
+    warm-up (nvidia-smi needs ~1 s to come up), sampled every 20 ms; only samples whose timestamp falls inside
+    the timed region are kept."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -64,7 +66,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -72,27 +74,38 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
-    def stop(self):
+    def wait_ready(self, timeout=5.0):
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t_start, t_end):
         if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            self.proc.kill()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm, mx, pw, reasons = [], [], [], set()
+        for ts, r in self.rows:
+            if ts < t_start or ts > t_end + 0.03:
+                continue
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def cpu_reference_run(frames_rows, threads, steps, warmup):
@@ -183,21 +196,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank); sampler.start()
     for _ in range(max(3, args.warmup)):
         step_device()
     launches_per_batch = ctx.last_launch_count()
     batches_per_step = (F + FB - 1) // FB
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
+    sampler.wait_ready()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    t_start = time.time()
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
     e1.record(stream)
     barrier()
+    t_end = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_start, t_end)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -271,7 +287,8 @@ def main():
     alg_bytes = 3 * W * H * FB
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))["dram_bytes_per_launch"]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "latest_traffic.json")))
+        traffic = tj["dram_bytes_per_launch"] * FB / tj["frames_per_launch"]     # ncu capture of one 16-frame launch
     except Exception:
         pass
     roofline = {"bound": "int_alu", "achieved": achieved, "peak": p_int, "unit": "Tiop/s", "frac": achieved / p_int,
