@@ -117,6 +117,16 @@ int  sadgpu_compute_device_batch(sadgpu_ctx *ctx, int device, int n_frames,
                                  uint8_t *dOut, size_t pitch_out, size_t frame_stride_out,
                                  void *cuda_stream, const sadgpu_tuning *tuning);
 
+/* Go-exact 8-bit luma of an interleaved 8-bit pixel plane on the device — what the reference
+ * does to a decoded PNG before the SAD path: mode 0 = NRGBA (pkg/despair/gray.go:43-58 generic path ==
+ * color.GrayModel.Convert, pkg/camera/output.go:145,160; channels 4, or 3 = opaque), mode 1 = opaque RGB with the
+ * intended 16-bit formula, mode 2 = convertRGBAToGray as written (gray.go:20-40: 8-bit values >> 24, always 0). */
+#define SADGPU_GRAY_NRGBA8         0
+#define SADGPU_GRAY_RGB8_INTENDED  1
+#define SADGPU_GRAY_RGBX8_LOADPNG  2
+int  sadgpu_gray_device(sadgpu_ctx *ctx, int device, const uint8_t *dSrc, size_t src_pitch, int channels, int mode,
+                        int w, int h, uint8_t *dGray, size_t gray_pitch, void *cuda_stream);
+
 /* Pinned host memory from the context's pool: frames that already live here are uploaded
  * without the staging memcpy (cameras write straight into it). */
 void *sadgpu_host_alloc(sadgpu_ctx *ctx, size_t bytes);

@@ -5,6 +5,7 @@
 #include "sad_kernels.cuh"
 #include "sad_fast.cuh"
 #include "sad_ws.cuh"
+#include "gray_kernels.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -646,6 +647,28 @@ int sadgpu_compute_device(sadgpu_ctx* c, int device, const uint8_t* dL, size_t p
 {
     return sadgpu_compute_device_batch(c, device, 1, dL, pitch_l, 0, dR, pitch_r, 0, w, h, B, D, y0, y1,
                                        dOut, pitch_out, 0, cuda_stream, tuning);
+}
+
+int sadgpu_gray_device(sadgpu_ctx* c, int device, const uint8_t* dSrc, size_t src_pitch, int channels, int mode,
+                       int w, int h, uint8_t* dGray, size_t gray_pitch, void* cuda_stream)
+{
+    if (!c || !dSrc || !dGray || w <= 0 || h <= 0) return SADGPU_EINVAL;
+    if (device < 0 || device >= (int)c->devices.size()) return SADGPU_ERANGE;
+    if ((channels != 3 && channels != 4) || mode < 0 || mode > 2) return SADGPU_EINVAL;
+    if (mode == GRAY_RGB8_INTENDED && channels != 3) return SADGPU_EINVAL;
+    if (src_pitch < (size_t)w * channels || gray_pitch < (size_t)w) return SADGPU_EINVAL;
+    cudaError_t e = cudaSetDevice(c->devices[device]);
+    if (e != cudaSuccess) return (int)e;
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    const int vec_ok = ((uintptr_t)dSrc % 16 == 0 && src_pitch % 16 == 0 && (uintptr_t)dGray % 4 == 0 && gray_pitch % 4 == 0) ? 1 : 0;
+    dim3 block(128), grid(ceil_div(ceil_div(w, 4), 128), h);
+    if (channels == 4 && mode == GRAY_NRGBA8)             gray_kernel<GRAY_NRGBA8, 4><<<grid, block, 0, s>>>(dSrc, src_pitch, dGray, gray_pitch, w, h, vec_ok);
+    else if (channels == 3 && mode == GRAY_NRGBA8)        gray_kernel<GRAY_NRGBA8, 3><<<grid, block, 0, s>>>(dSrc, src_pitch, dGray, gray_pitch, w, h, vec_ok);
+    else if (channels == 3 && mode == GRAY_RGB8_INTENDED) gray_kernel<GRAY_RGB8_INTENDED, 3><<<grid, block, 0, s>>>(dSrc, src_pitch, dGray, gray_pitch, w, h, vec_ok);
+    else if (channels == 4)                               gray_kernel<GRAY_RGBX8_LOADPNG, 4><<<grid, block, 0, s>>>(dSrc, src_pitch, dGray, gray_pitch, w, h, vec_ok);
+    else                                                  gray_kernel<GRAY_RGBX8_LOADPNG, 3><<<grid, block, 0, s>>>(dSrc, src_pitch, dGray, gray_pitch, w, h, vec_ok);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? SADGPU_OK : (int)e;
 }
 
 void* sadgpu_host_alloc(sadgpu_ctx* c, size_t bytes)

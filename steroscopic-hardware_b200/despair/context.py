@@ -101,6 +101,10 @@ class Context:
                                                      w, h, block_size, max_disparity, y0, y1, dOut, pitch_out, fs_out,
                                                      cuda_stream, tp))
 
+    def gray_device(self, dSrc, src_pitch, channels, mode, w, h, dGray, gray_pitch, device=0, cuda_stream=0):
+        """Go-exact luma on the device (modes: 0 NRGBA generic path, 1 opaque RGB intended, 2 LoadPNG-as-written)."""
+        N.check(self._L.sadgpu_gray_device(self._h, device, dSrc, src_pitch, channels, mode, w, h, dGray, gray_pitch, cuda_stream))
+
     # -- pinned pool -----------------------------------------------------------------------
     def host_array(self, shape):
         n = int(np.prod(shape))

@@ -251,3 +251,28 @@ def test_error_codes(ctx):
     with pytest.raises(despair.SadGpuError) as e:
         ctx.wait(12345 << 16, L)
     assert e.value.code == -4
+
+
+def test_go_exact_gray_conversion_on_gpu(torch_mod, ctx):
+    """the GPU luma kernel against the Go-exact formulas of oracle/go_image.py."""
+    torch = torch_mod
+    from oracle.go_image import _luma16
+    rng = np.random.default_rng(12)
+    for (h, w) in [(37, 101), (64, 256), (5, 3)]:
+        rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        rgba[..., 3] = rng.choice([255, 254, 251, 128, 0, 1], size=(h, w))          # testdata alpha minimum is 251-254
+        a = rgba.astype(np.uint64)
+        c16 = lambda c: (c * 257 * a[..., 3]) // 255
+        exp = _luma16(c16(a[..., 0]), c16(a[..., 1]), c16(a[..., 2]))
+        d = torch.from_numpy(rgba).cuda(); g = torch.zeros((h, w), dtype=torch.uint8, device="cuda")
+        ctx.gray_device(d.data_ptr(), w * 4, 4, 0, w, h, g.data_ptr(), w, cuda_stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(g.cpu().numpy(), exp)
+        rgb = np.ascontiguousarray(rgba[..., :3]); b = rgb.astype(np.uint64)
+        d3 = torch.from_numpy(rgb).cuda()
+        ctx.gray_device(d3.data_ptr(), w * 3, 3, 1, w, h, g.data_ptr(), w, cuda_stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(g.cpu().numpy(), _luma16(b[..., 0] * 257, b[..., 1] * 257, b[..., 2] * 257))
+        ctx.gray_device(d3.data_ptr(), w * 3, 3, 2, w, h, g.data_ptr(), w, cuda_stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert not g.cpu().numpy().any()                                               # gray.go:35-37 as written
