@@ -61,7 +61,8 @@ typedef struct sadgpu_tuning {
     int band_rows;          /* BH: output rows per CTA band                           */
     int groups_per_chunk;   /* disparity groups (4 disparities each) per CTA chunk     */
     int kernel_variant;     /* 0 = auto, 1 = generic (any block size), 2 = register-ring fast path (block_size <= 15),
-                               3 = warp-specialised fast path (block_size <= 9, max_disparity >= 68) */
+                               3 = warp-specialised fast path (block_size <= 9, max_disparity >= 68),
+                               4 = large-window kernel (block_size 16..31) */
     int reserved[4];        /* reserved[0]: frames per launch, used by sadgpu_plan_describe only */
 } sadgpu_tuning;
 

@@ -5,6 +5,7 @@
 #include "sad_kernels.cuh"
 #include "sad_fast.cuh"
 #include "sad_ws.cuh"
+#include "sad_wide.cuh"
 #include "gray_kernels.cuh"
 
 #include <algorithm>
@@ -174,6 +175,21 @@ cudaError_t launch_ws(const FastPlan& p, cudaStream_t s, bool* attr_done)
     return cudaGetLastError();
 }
 
+template <int HALF>
+cudaError_t launch_wide(const FastPlan& p, cudaStream_t s, bool* attr_done)
+{
+    using C = WideCfg<HALF>;
+    static_assert(C::SMEM <= kSmemBudget, "wide kernel does not fit shared memory");
+    auto k = sad_wide_kernel<HALF>;
+    if (!*attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return e;
+        *attr_done = true;
+    }
+    k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    return cudaGetLastError();
+}
+
 typedef cudaError_t (*fast_fn)(const FastPlan&, cudaStream_t, bool*);
 struct FastEntry { fast_fn fn; int nt, smem, rb; };
 template <int HALF, int NGC> constexpr FastEntry fast_entry()
@@ -198,7 +214,12 @@ const FastEntry kWs[5] = {
     FastEntry{launch_ws<2>, WsCfg<2>::NT, WsCfg<2>::SMEM, WsCfg<2>::RB}, FastEntry{launch_ws<3>, WsCfg<3>::NT, WsCfg<3>::SMEM, WsCfg<3>::RB},
     FastEntry{launch_ws<4>, WsCfg<4>::NT, WsCfg<4>::SMEM, WsCfg<4>::RB}};
 
+// slot 4 = large-window kernel (sad_wide.cuh): h = 8..15, chunks of 8 groups
+#define WIDE_ENTRY(H) FastEntry{launch_wide<H>, WideCfg<H>::NT, WideCfg<H>::SMEM, WideCfg<H>::RB}
+const FastEntry kWide[8] = {WIDE_ENTRY(8), WIDE_ENTRY(9), WIDE_ENTRY(10), WIDE_ENTRY(11), WIDE_ENTRY(12), WIDE_ENTRY(13), WIDE_ENTRY(14), WIDE_ENTRY(15)};
+
 bool fast_supported(int B) { return B / 2 <= 7; }
+bool wide_supported(int B) { return B / 2 >= 8 && B / 2 <= 15; }
 bool ws_supported(int B, int D) { return B / 2 <= 4 && (D + 4) / 4 > 17; }
 
 int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, const sadgpu_tuning* t, int sm_count,
@@ -206,22 +227,24 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
 {
     int rc = validate(w, h, B, D, y0, y1);
     if (rc) return rc;
-    if (!fast_supported(B) || n_frames < 1) return SADGPU_EINVAL;
+    if ((!fast_supported(B) && !wide_supported(B)) || n_frames < 1) return SADGPU_EINVAL;
     const int half = B / 2;
+    const bool wide = wide_supported(B);
     FastArgs& a = p->a;
     memset(&a, 0, sizeof(a));
     a.W = w; a.H = h; a.y0 = y0; a.y1 = y1; a.D = D;
     a.NG = (D + 4) / 4;
     int slot = a.NG <= 9 ? 0 : a.NG <= 17 ? 1 : 2;
-    if (!kFast[half][slot].fn) slot = 1;
+    if (!wide && !kFast[half][slot].fn) slot = 1;
     if (t && t->groups_per_chunk > 0) {                     // tests: force smaller chunks
         slot = t->groups_per_chunk <= 9 ? 0 : t->groups_per_chunk <= 17 ? 1 : slot;
     }
-    const bool ws = want_ws && ws_supported(B, D);
+    const bool ws = !wide && want_ws && ws_supported(B, D);
     if (ws) slot = 3;
-    const FastEntry& fe = ws ? kWs[half] : kFast[half][slot];
+    if (wide) slot = 4;
+    const FastEntry& fe = wide ? kWide[half - 8] : ws ? kWs[half] : kFast[half][slot];
     const int tw = ws ? 32 : 64;
-    p->half = half; p->ngc = ws ? 33 : kFastNgc[slot]; p->rb = fe.rb;
+    p->half = half; p->ngc = wide ? 8 : ws ? 33 : kFastNgc[slot]; p->rb = fe.rb;
     a.NC = ceil_div(a.NG, p->ngc);
     p->nthreads = fe.nt; p->smem = fe.smem;
     const int rows = std::max(1, y1 - y0);
@@ -273,7 +296,7 @@ struct sadgpu_ctx {
     std::mutex pool_mu;
     std::vector<std::pair<uint8_t*, size_t>> pool;
     bool attr_done[kMaxDevices][16];
-    bool fast_attr_done[kMaxDevices][8][4];
+    bool fast_attr_done[kMaxDevices][8][5];
     std::vector<size_t> dev_gkey_bytes;
     std::vector<uint32_t*> dev_gkey;       // per device scratch for sadgpu_compute_device
     std::mutex dev_mu;
@@ -316,10 +339,11 @@ int ensure_gkey(sadgpu_ctx* c, int dev_index, size_t bytes, uint32_t** out)
 int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, uint32_t* slot_gkey, cudaStream_t s)
 {
     const int variant = t ? t->kernel_variant : 0;
-    if (variant < 0 || variant > 3) return SADGPU_EINVAL;
+    if (variant < 0 || variant > 4) return SADGPU_EINVAL;
     if (variant == 2 && !fast_supported(j.B)) return SADGPU_EINVAL;
     if (variant == 3 && !ws_supported(j.B, j.D)) return SADGPU_EINVAL;
-    const bool use_fast = variant >= 2 || (variant == 0 && fast_supported(j.B));
+    if (variant == 4 && !wide_supported(j.B)) return SADGPU_EINVAL;
+    const bool use_fast = variant >= 2 || (variant == 0 && (fast_supported(j.B) || wide_supported(j.B)));
     const bool want_ws = variant == 3 || variant == 0;
     int launches = 0;
     if (use_fast) {
@@ -342,7 +366,8 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
             a.gkey = gk;
             sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 8192), 256, 0, s>>>(gk, n, 0xFFFFFFFFu);
         }
-        cudaError_t e = slot == 3 ? kWs[p.half].fn(p, s, &c->fast_attr_done[dev_index][p.half][3])
+        cudaError_t e = slot == 4 ? kWide[p.half - 8].fn(p, s, &c->fast_attr_done[dev_index][p.half - 8][4])
+                      : slot == 3 ? kWs[p.half].fn(p, s, &c->fast_attr_done[dev_index][p.half][3])
                                   : kFast[p.half][slot].fn(p, s, &c->fast_attr_done[dev_index][p.half][slot]);
         if (e != cudaSuccess) return (int)e;
         if (a.NC > 1) {
@@ -704,7 +729,8 @@ int sadgpu_last_launch_count(sadgpu_ctx* c) { return c ? c->last_launches.load()
 int sadgpu_plan_describe(int w, int h, int B, int D, int y0, int y1, const sadgpu_tuning* t, char* buf, size_t buflen)
 {
     const int variant = t ? t->kernel_variant : 0;
-    if (variant >= 2 || (variant == 0 && fast_supported(B))) {
+    if (variant > 4 || (variant == 2 && !fast_supported(B)) || (variant == 4 && !wide_supported(B))) return SADGPU_EINVAL;
+    if (variant >= 2 || (variant == 0 && (fast_supported(B) || wide_supported(B)))) {
         FastPlan p; int slot = 0;
         const int nf = t && t->reserved[0] > 0 ? t->reserved[0] : 1;       // reserved[0]: frames per launch (describe only)
         int rc = make_fast_plan(w, h, B, D, y0, y1, nf, t, 148, &p, &slot, variant == 3 || variant == 0);
@@ -714,7 +740,7 @@ int sadgpu_plan_describe(int w, int h, int B, int D, int y0, int y1, const sadgp
             snprintf(buf, buflen,
                      "{\"variant\":\"%s\",\"half\":%d,\"NG\":%d,\"NC\":%d,\"NGc\":%d,\"TW\":%d,\"RB\":%d,\"BH\":%d,"
                      "\"grid\":[%u,%u,%u],\"threads\":%d,\"smem\":%zu,\"launches\":%d,\"frames_per_launch\":%d}",
-                     slot == 3 ? "warp-specialised" : "fast", p.half, p.a.NG, p.a.NC, p.ngc, slot == 3 ? 32 : 64, p.rb, p.a.BH,
+                     slot == 4 ? "wide" : slot == 3 ? "warp-specialised" : "fast", p.half, p.a.NG, p.a.NC, p.ngc, slot == 3 ? 32 : 64, p.rb, p.a.BH,
                      p.grid.x, p.grid.y, p.grid.z, p.nthreads, p.smem, p.launches, nf);
         return SADGPU_OK;
     }

@@ -88,19 +88,23 @@ def test_tilings_do_not_change_pixels(torch_mod, ctx, oracle):
         L, R = synth_pair(rng, H, W, i % 5)
         tun = dict(rows_per_batch=int(rng.integers(1, 12)), band_rows=int(rng.integers(1, 50)),
                    groups_per_chunk=int(rng.integers(1, 21)), kernel_variant=1 if (i % 2 or B > 15) else 2)
+        if B > 15 and i % 2 == 0:
+            tun = dict(band_rows=int(rng.integers(1, 50)), kernel_variant=4)
         if B <= 9 and D >= 68 and i % 3 == 0:
             tun = dict(band_rows=int(rng.integers(1, 50)), kernel_variant=3)
         assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, tun), oracle.frame_box(L, R, B, D)), (W, H, B, D, tun)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_every_kernel_variant_agrees_with_oracle(torch_mod, ctx, oracle, variant):
     """variant 1 = generic shared-memory-ring kernel (any block size), 2 = register-ring fast path (B <= 15),
-    3 = warp-specialised double-buffered kernel (B <= 9, D > 64)."""
+    3 = warp-specialised double-buffered kernel (B <= 9, D >= 68), 4 = large-window kernel (B 16..31)."""
     rng = np.random.default_rng(60 + variant)
     for i in range(24):
         W = int(rng.integers(20, 400)); H = int(rng.integers(10, 100))
-        if variant == 3:
+        if variant == 4:
+            B = int(rng.integers(16, 32)); D = int(rng.choice([7, 16, 33, 64, 128, 200, 256]))
+        elif variant == 3:
             B = int(rng.integers(1, 10)); D = int(rng.choice([68, 100, 128, 129, 200, 256]))
         else:
             B = int(rng.integers(1, 16)); D = int(rng.choice([7, 16, 33, 64, 128, 200, 256]))

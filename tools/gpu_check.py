@@ -40,6 +40,10 @@ def main():
             tun = dict(tun or {}); tun['kernel_variant'] = 2
         if B <= 9 and D >= 68 and i % 4 == 1:
             tun = dict(tun or {}); tun['kernel_variant'] = 3
+        if B >= 16 and i % 2 == 0:
+            tun = dict(band_rows=(tun or {}).get('band_rows', 0), kernel_variant=4)
+        if B >= 16 and i % 2 == 1:
+            tun = dict(tun or {}); tun['kernel_variant'] = 1
         got = dev_run(ctx, L, R, B, D, tun)
         ncase += 1
         if not np.array_equal(got, exp):
