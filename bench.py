@@ -312,7 +312,7 @@ def main():
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload,
             "frames_per_sec": args.steps * F * world / (ms_max * 1e-3), "us_per_frame_per_gpu": us_per_frame,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * F, "d2h_bytes_per_step": W * H * F,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * F * world, "d2h_bytes_per_step": W * H * F * world,
                     "frames_per_sec": e2e_steps * F * world / float(t.item()), "parity": e2e_parity,
                     "how": f"sadgpu_submit/sadgpu_wait, pinned host buffers, {n_streams} streams in flight"},
             "gpu_launches": args.steps * batches_per_step * launches_per_batch, "frames_per_launch": FB,

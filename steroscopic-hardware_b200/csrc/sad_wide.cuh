@@ -7,7 +7,8 @@
 //   * vertical sums are 32-bit: the packed difference of the two rows is formed in one IADD3 with a per-lane bias
 //     (H <= 7905 < 2^13, so n + 0x20002000 - o never borrows across the 16-bit lanes) and unpacked;
 //     keys are sum*512 + d (IMAD);
-//   * a row walk is split into two 32-output segments so that a 9-row x 8-group batch still has enough items.
+//   * a row walk is split into 2 or 4 segments (32 / 16 outputs) so that a 12-row x 8-group batch still has enough
+//     items to occupy the CTA's 512 threads (phase B: one thread per (column, group)).
 // The disparity range is processed in chunks of 8 groups (32 disparities) merged by atomicMin on the key map.
 #pragma once
 #include <cstdint>
@@ -20,12 +21,12 @@ template <int HALF> struct WideCfg {
     static_assert(HALF >= 8 && HALF <= 15, "wide kernel: block_size 16..31");
     static constexpr int WIN = 2 * HALF + 1;
     static constexpr int TW = 64, TWP = 65;
-    static constexpr int SEG = 2, SEGW = TW / SEG;                  // walk segments per row
+    static constexpr int SEG = HALF >= 12 ? 4 : 2, SEGW = TW / SEG;  // walk segments per row (more items per batch for the widest windows)
     static constexpr int NSTEP = TW + 2 * HALF;                     // columns of L a row needs
     static constexpr int SSTEP = SEGW + 2 * HALF;                   // steps of one segment walk
     static constexpr int LW = (NSTEP + 3) & ~3;
-    static constexpr int NGC = 8, GT = 2, K = NGC / GT;             // groups per chunk / per phase-B thread / threads per column
-    static constexpr int NT = TW * K;                               // 256
+    static constexpr int NGC = 8, GT = 1, K = NGC / GT;             // groups per chunk / per phase-B thread / threads per column
+    static constexpr int NT = TW * K;                               // 512
     static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
     static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;
     static constexpr int RW = NGC - 1 + NWALKW;
