@@ -47,11 +47,14 @@ def test_plans_cover_the_parameter_surface(native):
                 assert p["grid"][0] * p["TW"] >= 1920
                 if p["variant"] == "generic":
                     assert p["TW"] == p["NSTEP"] - 2 * (B // 2)
+                elif p["variant"] == "wide":
+                    assert 16 <= B <= 31
                 else:
                     assert B <= 15
     assert despair.plan_describe(1920, 1080, 9, 128)["variant"] == "warp-specialised"
     assert despair.plan_describe(1920, 1080, 15, 256)["variant"] == "fast"
-    assert despair.plan_describe(1920, 1080, 31, 256)["variant"] == "generic"
+    assert despair.plan_describe(1920, 1080, 31, 256)["variant"] == "wide"
+    assert despair.plan_describe(1920, 1080, 31, 256, tuning=dict(kernel_variant=1))["variant"] == "generic"
     with pytest.raises(despair.SadGpuError):
         despair.plan_describe(1920, 1080, 31, 256, tuning=dict(kernel_variant=2))      # fast path needs block_size <= 15
 
