@@ -280,3 +280,23 @@ def test_go_exact_gray_conversion_on_gpu(torch_mod, ctx):
         ctx.gray_device(d3.data_ptr(), w * 3, 3, 2, w, h, g.data_ptr(), w, cuda_stream=torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         assert not g.cpu().numpy().any()                                               # gray.go:35-37 as written
+
+
+def test_row_band_sharding_across_devices(torch_mod, oracle):
+    """cfg4-style: one frame split into row bands with a block-size halo over every visible GPU of the box
+    (sadgpu_compute_sharded), host-side gather; frames of a stream round-robin over devices (stream s -> device s % n)."""
+    import despair
+    n = torch_mod.cuda.device_count()
+    devs = list(range(min(n, 8)))
+    c = despair.Context(devs, 640, 400, max(2, len(devs)))
+    rng = np.random.default_rng(21)
+    L, R = synth_pair(rng, 400, 640, 1)
+    exp = oracle.frame_box(L, R, 31, 64)
+    assert np.array_equal(c.compute_sharded(L, R, 31, 64), exp)
+    outs = [np.zeros_like(L) for _ in devs]
+    ts = [c.submit(L, R, 9, 128, stream=s) for s in range(len(devs))]        # stream s lives on device s % n
+    for s, t in enumerate(ts):
+        c.wait(t, outs[s])
+    exp2 = oracle.frame_box(L, R, 9, 128)
+    assert all(np.array_equal(o, exp2) for o in outs)
+    c.close()
