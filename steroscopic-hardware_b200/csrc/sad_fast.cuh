@@ -41,7 +41,7 @@ template <int HALF> struct FastTraits {
 template <int HALF, int NGC> struct FastCfg : FastTraits<HALF> {
     using T = FastTraits<HALF>;
     // groups per phase-B thread: bounded by the register ring (2*GT*WIN registers)
-    static constexpr int GT = HALF <= 4 ? (NGC == 33 ? 5 : 3) : 2;
+    static constexpr int GT = HALF <= 4 ? (NGC == 33 ? 5 : 3) : (NGC == 18 ? 3 : 2);
     static constexpr int K = (NGC + GT - 1) / GT;                   // phase-B threads per column
     static constexpr int NGP = K * GT;                              // group slots in H
     static constexpr int NT = T::TW * K;                            // threads per CTA

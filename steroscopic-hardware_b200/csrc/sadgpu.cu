@@ -197,16 +197,16 @@ template <int HALF, int NGC> constexpr FastEntry fast_entry()
     return FastEntry{launch_fast<HALF, NGC>, FastCfg<HALF, NGC>::NT, FastCfg<HALF, NGC>::SMEM, FastCfg<HALF, NGC>::RB};
 }
 // index [half][slot], slot 0/1/2 = 9/17/33 groups per chunk; h >= 5 has no 33-group instance (shared memory)
-const int kFastNgc[3] = {9, 17, 33};
+const int kFastNgc[3] = {9, 17, 33};       // h >= 5 uses 18 in slot 1 (3 groups per phase-B thread, 384 threads: no register spills)
 const FastEntry kFast[8][3] = {
     {fast_entry<0, 9>(), fast_entry<0, 17>(), fast_entry<0, 33>()},
     {fast_entry<1, 9>(), fast_entry<1, 17>(), fast_entry<1, 33>()},
     {fast_entry<2, 9>(), fast_entry<2, 17>(), fast_entry<2, 33>()},
     {fast_entry<3, 9>(), fast_entry<3, 17>(), fast_entry<3, 33>()},
     {fast_entry<4, 9>(), fast_entry<4, 17>(), fast_entry<4, 33>()},
-    {fast_entry<5, 9>(), fast_entry<5, 17>(), FastEntry{nullptr, 0, 0, 0}},
-    {fast_entry<6, 9>(), fast_entry<6, 17>(), FastEntry{nullptr, 0, 0, 0}},
-    {fast_entry<7, 9>(), fast_entry<7, 17>(), FastEntry{nullptr, 0, 0, 0}}};
+    {fast_entry<5, 9>(), fast_entry<5, 18>(), FastEntry{nullptr, 0, 0, 0}},
+    {fast_entry<6, 9>(), fast_entry<6, 18>(), FastEntry{nullptr, 0, 0, 0}},
+    {fast_entry<7, 9>(), fast_entry<7, 18>(), FastEntry{nullptr, 0, 0, 0}}};
 
 // slot 3 = warp-specialised kernel (sad_ws.cuh): h <= 4, 33-group chunks, 32-column strips
 const FastEntry kWs[5] = {
@@ -234,7 +234,7 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
     memset(&a, 0, sizeof(a));
     a.W = w; a.H = h; a.y0 = y0; a.y1 = y1; a.D = D;
     a.NG = (D + 4) / 4;
-    int slot = a.NG <= 9 ? 0 : a.NG <= 17 ? 1 : 2;
+    int slot = a.NG <= 9 ? 0 : a.NG <= (half >= 5 ? 18 : 17) ? 1 : 2;
     if (!wide && !kFast[half][slot].fn) slot = 1;
     if (t && t->groups_per_chunk > 0) {                     // tests: force smaller chunks
         slot = t->groups_per_chunk <= 9 ? 0 : t->groups_per_chunk <= 17 ? 1 : slot;
@@ -244,7 +244,7 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
     if (wide) slot = 4;
     const FastEntry& fe = wide ? kWide[half - 8] : ws ? kWs[half] : kFast[half][slot];
     const int tw = ws ? 32 : 64;
-    p->half = half; p->ngc = wide ? 8 : ws ? 33 : kFastNgc[slot]; p->rb = fe.rb;
+    p->half = half; p->ngc = wide ? 8 : ws ? 33 : (slot == 1 && half >= 5) ? 18 : kFastNgc[slot]; p->rb = fe.rb;
     a.NC = ceil_div(a.NG, p->ngc);
     p->nthreads = fe.nt; p->smem = fe.smem;
     const int rows = std::max(1, y1 - y0);

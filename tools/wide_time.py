@@ -8,7 +8,7 @@ rng = np.random.default_rng(1)
 Ln = rng.integers(0,256,(Hh,Ww),dtype=np.uint8); Rn = np.roll(Ln,-20,1)
 L = torch.from_numpy(Ln).cuda().unsqueeze(0).repeat(F,1,1).contiguous(); R = torch.from_numpy(Rn).cuda().unsqueeze(0).repeat(F,1,1).contiguous(); Oo = torch.zeros_like(L)
 st = torch.cuda.current_stream().cuda_stream
-for (B, D) in [(31,256),(31,64),(17,256),(17,128),(21,256),(16,64)]:
+for (B, D) in [(15,256),(15,128),(15,64),(13,256),(11,256),(11,128),(11,64)]:
     run = lambda: ctx.compute_device_batch(F, L.data_ptr(), Ww, Ww*Hh, R.data_ptr(), Ww, Ww*Hh, Ww, Hh, B, D, Oo.data_ptr(), Ww, Ww*Hh, cuda_stream=st)
     for _ in range(2): run()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
