@@ -300,3 +300,14 @@ def test_row_band_sharding_across_devices(torch_mod, oracle):
     exp2 = oracle.frame_box(L, R, 9, 128)
     assert all(np.array_equal(o, exp2) for o in outs)
     c.close()
+
+
+@pytest.mark.parametrize("variant,B,D", [(1, 21, 40), (2, 13, 64), (2, 9, 16), (3, 9, 128), (3, 5, 200), (4, 31, 256), (4, 16, 33)])
+def test_unaligned_pitch_and_odd_widths(torch_mod, ctx, oracle, variant, B, D):
+    """Pitches that are not multiples of 4 disable the aligned 32-bit tile loads; widths that are not multiples of the
+    strip width exercise the right-edge masking (sad.go:231-233) in every kernel."""
+    rng = np.random.default_rng(70 + variant + B)
+    for (H, W, pad) in [(33, 131, 3), (20, 257, 1), (41, 64, 5), (17, 95, 2)]:
+        L, R = synth_pair(rng, H, W, 1)
+        got = dev_run(torch_mod, ctx, L, R, B, D, dict(kernel_variant=variant), pitch_pad=pad)
+        assert np.array_equal(got, oracle.frame_box(L, R, B, D)), (H, W, pad, variant, B, D)
