@@ -63,7 +63,8 @@ typedef struct sadgpu_tuning {
     int kernel_variant;     /* 0 = auto, 1 = generic (any block size), 2 = register-ring fast path (block_size <= 15),
                                3 = warp-specialised fast path (block_size <= 9, max_disparity >= 68),
                                4 = large-window kernel (block_size 16..31) */
-    int reserved[4];        /* reserved[0]: frames per launch, used by sadgpu_plan_describe only */
+    int reserved[4];        /* [0]: frames per launch (sadgpu_plan_describe only); [1]: developer flags (role idling, cycle counters);
+                               [2] = 1: do not use TMA tile loads in the warp-specialised kernel */
 } sadgpu_tuning;
 
 int  sadgpu_device_count(void);

@@ -11,17 +11,20 @@
 //     is many waves deep and the single-wave tail disappears.
 #pragma once
 #include <cstdint>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 namespace sadgpu {
 
 struct FastArgs {
+    CUtensorMap tmapL, tmapR;                // TMA descriptors (warp-specialised kernel, use_tma != 0); 64-byte aligned, first members
     const uint8_t* L; const uint8_t* R; uint8_t* out; uint32_t* gkey;
     long long frameL, frameR, frameOut;      // byte strides between frames of a batch
     int pitchL, pitchR, pitchOut;
     int W, H, y0, y1;
     int D, NG, NC, BH;
     int aligned;                             // R rows may be fetched with aligned 32-bit loads
+    int use_tma;                             // tile loads by cp.async.bulk.tensor (needs 16-byte aligned base / pitch / frame stride)
     int debug_skip;                          // developer experiments: 1 = walkers idle, 2 = consumers idle (results wrong)
     unsigned k65536;                         // = 65536, passed at run time so that v*65536+idx stays an IMAD (FMA pipe)
 };

@@ -39,13 +39,21 @@ template <int HALF> struct WsCfg {
     static constexpr int RW = NGC - 1 + NWALKW;
     static constexpr int H_BYTES = ((RB * NGC * TWP * 8 + 15) / 16) * 16;      // one buffer
     static constexpr int L_BYTES = RB * LW * 4;
-    static constexpr int R_BYTES = ((RB * RW * 4 + 15) / 16) * 16;
+    // TMA needs the innermost start coordinate on a 16-byte boundary: the right tile starts up to 12 bytes early (RWT words
+    // per row), the raw left tile LSH bytes early (x0 is a multiple of 32, so LSH only depends on h).
+    static constexpr int RWT = ((RW * 4 + 12 + 15) / 16) * 4;
+    static constexpr int R_BYTES = ((RB * RWT * 4 + 127) / 128) * 128;        // 128-byte multiple: each buffer is a TMA destination
+    static constexpr int LSH = (16 - HALF % 16) % 16;
+    static constexpr int LBOX = ((LSH + NSTEP + 15) / 16) * 16;               // TMA box width of the raw left tile (bytes)
+    static constexpr int LRAW_BYTES = ((RB * LBOX + 127) / 128) * 128;
     static constexpr int PK_BYTES = RB * K * TW * 4;
-    static constexpr int OFF_L = 2 * H_BYTES;
-    static constexpr int OFF_R = OFF_L + NTILE * L_BYTES;
-    static constexpr int OFF_PK = OFF_R + NTILE * R_BYTES;
+    static constexpr int OFF_R = ((2 * H_BYTES + 127) / 128) * 128;            // TMA destinations first (128-byte aligned)
+    static constexpr int OFF_LRAW = OFF_R + NTILE * R_BYTES;
+    static constexpr int OFF_L = OFF_LRAW + NTILE * LRAW_BYTES;
+    static constexpr int OFF_PK = OFF_L + NTILE * L_BYTES;
     static constexpr int OFF_LUT = OFF_PK + 2 * PK_BYTES;
-    static constexpr int SMEM = OFF_LUT + 1040;
+    static constexpr int OFF_MBAR = OFF_LUT + 1040;
+    static constexpr int SMEM = OFF_MBAR + 64;
     static_assert(WIN <= RB, "register ring shorter than the window");
     static_assert(NT * REGS_LAUNCH <= 65536 && 384 * REGS_PROD + 384 * REGS_CONS <= NT * REGS_LAUNCH, "register budget");
     static_assert(GT * K == NGC && W_CONS + K <= 24, "warp roles");
@@ -140,11 +148,11 @@ __device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __res
 }
 
 template <int HALF>
-__global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastArgs a)
+__global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid_constant__ FastArgs a)
 {
     using C = WsCfg<HALF>;
     constexpr int WIN = C::WIN, TW = C::TW, TWP = C::TWP, RB = C::RB, GT = C::GT, K = C::K, NGC = C::NGC;
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     uint2* Hs = reinterpret_cast<uint2*>(smem);                                   // [2][RB][NGC][TWP]
     uint32_t* Lrep = reinterpret_cast<uint32_t*>(smem + C::OFF_L);               // [2][RB][LW]
     uint32_t* Ral = reinterpret_cast<uint32_t*>(smem + C::OFF_R);                // [2][RB][RW]
@@ -192,8 +200,58 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastAr
                 __syncthreads();
             }
         } else if (warp > C::W_FIN) {
-            __syncthreads();
-            for (int it = 0; it < nb + 2; ++it) __syncthreads();       // spare warp of the producer register class
+            // ---- warp 11: TMA tile loader (a.use_tma) — two cp.async.bulk.tensor per batch (raw left rows, aligned right
+            //      rows; hardware zero-fill outside the image), completion on an mbarrier, then the left pixels are
+            //      replicated into Lrep.  Without TMA this warp idles and the walkers prefetch their own rows. ----
+            if (a.use_tma) {
+                uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::OFF_MBAR);
+                const uint32_t mbar0 = (uint32_t)__cvta_generic_to_shared(mbar);
+                const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;
+                const int xr0a = xr0 - (((xr0 % 16) + 16) % 16);                // 16-byte aligned start of the right tile
+                if (lane == 0) {
+#pragma unroll
+                    for (int t = 0; t < C::NTILE; ++t) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar0 + 8 * t));
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                }
+                __syncwarp();
+                auto load = [&](int batch) {
+                    const int tb = batch % C::NTILE;
+                    const uint32_t bar = mbar0 + 8 * tb;
+                    const uint32_t dstR = (uint32_t)__cvta_generic_to_shared(smem + C::OFF_R + tb * C::R_BYTES);
+                    const uint32_t dstL = (uint32_t)__cvta_generic_to_shared(smem + C::OFF_LRAW + tb * C::LRAW_BYTES);
+                    const int y = r0 + batch * RB;
+                    if (lane == 0) {
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(RB * C::RWT * 4 + RB * C::LBOX) : "memory");
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                     :: "r"(dstR), "l"(&a.tmapR), "r"(xr0a), "r"(y), "r"(frame), "r"(bar) : "memory");
+                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                     :: "r"(dstL), "l"(&a.tmapL), "r"(x0 - HALF - C::LSH), "r"(y), "r"(frame), "r"(bar) : "memory");
+                    }
+                    // bounded wait on the phase of this buffer's (batch / NTILE)-th use; a stuck copy traps instead of hanging
+                    const uint32_t parity = (uint32_t)(batch / C::NTILE) & 1u;
+                    uint32_t done = 0;
+                    for (int spin = 0; spin < (1 << 24) && !done; ++spin)
+                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                    if (!done) __trap();
+                    const uint8_t* raw = smem + C::OFF_LRAW + tb * C::LRAW_BYTES;
+                    uint32_t* Ld = Lrep + tb * LBUF;
+                    for (int idx = lane; idx < RB * C::LW; idx += 32) {
+                        const int rb = idx / C::LW, i = idx - rb * C::LW;
+                        Ld[idx] = (uint32_t)raw[rb * C::LBOX + C::LSH + i] * 0x01010101u;
+                    }
+                };
+                load(0);
+                if (nb > 1) load(1);
+                __syncthreads();
+                for (int it = 0; it < nb + 2; ++it) {
+                    if (it + 2 < nb) load(it + 2);                 // tile buffer (it+2)%3 was last read in iteration it-1
+                    __syncthreads();
+                }
+            } else {
+                __syncthreads();
+                for (int it = 0; it < nb + 2; ++it) __syncthreads();
+            }
         } else {
             // ---- walkers: warp w < 9 walks row w for groups 0..31 and prefetches row w of the batch after next
             //      (L pixels replicated, R as aligned words) into the third tile buffer; warp 9 walks group 32
@@ -204,7 +262,9 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastAr
             const uint8_t* __restrict__ Lg = a.L + (long long)frame * a.frameL;
             const uint8_t* __restrict__ Rg = a.R + (long long)frame * a.frameR;
             const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;
-            constexpr int NLQ = (C::LW + 31) / 32, NRQ = (C::RW + 31) / 32;
+            const int xr0a = xr0 - (((xr0 % 16) + 16) % 16);                    // tile rows start 16-byte aligned (TMA rule), same layout without TMA
+            const int rext = (xr0 - xr0a) >> 2;                                 // words to skip at the start of a tile row
+            constexpr int NLQ = (C::LW + 31) / 32, NRQ = (C::RWT + 31) / 32;
             int lx[NLQ], rx[NRQ], rmode[NRQ];            // column of each slot of this lane; -1 / mode 0 = zero
 #pragma unroll
             for (int q = 0; q < NLQ; ++q) {
@@ -213,8 +273,8 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastAr
             }
 #pragma unroll
             for (int q = 0; q < NRQ; ++q) {
-                const int j = lane + 32 * q, x = xr0 + 4 * j;
-                const bool in = j < C::RW && x + 3 >= 0 && x < a.W;
+                const int j = lane + 32 * q, x = xr0a + 4 * j;
+                const bool in = j < C::RWT && x + 3 >= 0 && x < a.W;
                 rx[q] = x;
                 rmode[q] = !in ? 0 : (a.aligned && x >= 0 && x + 3 < a.W) ? 1 : 2;
             }
@@ -240,13 +300,14 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastAr
             };
             auto commit = [&](int batch) {
                 uint32_t* Ld = Lrep + (batch % C::NTILE) * LBUF + rb * C::LW;
-                uint32_t* Rd = Ral + (batch % C::NTILE) * RBUF + rb * C::RW;
+                uint32_t* Rd = Ral + (batch % C::NTILE) * RBUF + rb * C::RWT;
 #pragma unroll
                 for (int q = 0; q < NLQ; ++q) { const int i = lane + 32 * q; if (i < C::LW) Ld[i] = vl[q] * 0x01010101u; }
 #pragma unroll
-                for (int q = 0; q < NRQ; ++q) { const int j = lane + 32 * q; if (j < C::RW) Rd[j] = vr[q]; }
+                for (int q = 0; q < NRQ; ++q) { const int j = lane + 32 * q; if (j < C::RWT) Rd[j] = vr[q]; }
             };
-            if (!tail) {
+            const bool self_load = !tail && !a.use_tma;
+            if (self_load) {
                 issue(0); commit(0);
                 if (nb > 1) { issue(1); commit(1); }
             }
@@ -256,12 +317,12 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const FastAr
                 if (a.debug_skip & 4) { volatile uint8_t* vq = lut; tw += (long long)(vq[0] & 0) ; }   // forces the deferred barrier wait to complete
                 const long long c0 = clock64();
                 if ((a.debug_skip & 4) && it > 0) tb += c0 - cprev;
-                const bool pre = !tail && it + 2 < nb;
+                const bool pre = self_load && it + 2 < nb;
                 if (pre) issue(it + 2);
                 if (it < nb && act && (a.debug_skip & 3) != 1) {
                     const int buf = it & 1, tb = it % C::NTILE;
                     const uint32_t* Lr = Lrep + tb * LBUF + rb * C::LW;
-                    const uint32_t* Rr = Ral + tb * RBUF + rb * C::RW + (NGC - 1 - gl);
+                    const uint32_t* Rr = Ral + tb * RBUF + rb * C::RWT + rext + (NGC - 1 - gl);
                     uint2* Hout = Hs + buf * HBUF + (rb * NGC + gl) * TWP;
                     if (nvalid >= C::NSTEP) ws_walk<HALF, false>(Lr, Rr, Hout, nvalid);
                     else                    ws_walk<HALF, true>(Lr, Rr, Hout, nvalid);

@@ -270,6 +270,43 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
     return SADGPU_OK;
 }
 
+// ---- TMA descriptors for the warp-specialised kernel (driver entry point fetched through the runtime) ----
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn get_encode_tiled()
+{
+    static encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult st;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+            fn = (encode_tiled_fn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// 3-D uint8 tensor (x, y, frame) with a (box_w x box_h x 1) box, zero fill outside.  Returns false when TMA cannot be used.
+bool make_tmap(CUtensorMap* m, const uint8_t* base, int w, int h, size_t pitch, long long frame_stride, int n_frames, int box_w, int box_h)
+{
+    encode_tiled_fn enc = get_encode_tiled();
+    if (!enc) return false;
+    const unsigned long long fs = (n_frames > 1 && frame_stride > 0) ? (unsigned long long)frame_stride : (unsigned long long)pitch * h;
+    if ((uintptr_t)base % 16 || pitch % 16 || fs % 16 || box_w % 16 || box_w > 256 || box_h > 256) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n_frames};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fs};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int HALF> void ws_box(int* lbox, int* rbox, int* rb) { *lbox = WsCfg<HALF>::LBOX; *rbox = WsCfg<HALF>::RWT * 4; *rb = WsCfg<HALF>::RB; }
+
 struct Slot {
     int dev_index = 0, device = 0;
     cudaStream_t st = nullptr;
@@ -357,6 +394,16 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
         a.frameL = j.frameL; a.frameR = j.frameR; a.frameOut = j.frameOut;
         a.k65536 = 65536u;
         a.debug_skip = t ? t->reserved[1] : 0;
+        a.use_tma = 0;
+        if (slot == 3 && !(t && t->reserved[2] == 1)) {                 // reserved[2] == 1: force the non-TMA loader (tests)
+            int lbox = 0, rbox = 0, rb = 0;
+            switch (p.half) { case 0: ws_box<0>(&lbox, &rbox, &rb); break; case 1: ws_box<1>(&lbox, &rbox, &rb); break;
+                              case 2: ws_box<2>(&lbox, &rbox, &rb); break; case 3: ws_box<3>(&lbox, &rbox, &rb); break;
+                              default: ws_box<4>(&lbox, &rbox, &rb); }
+            if (make_tmap(&a.tmapL, j.dL, j.w, j.h, j.pitchL, j.frameL, j.n_frames, lbox, rb) &&
+                make_tmap(&a.tmapR, j.dR, j.w, j.h, j.pitchR, j.frameR, j.n_frames, rbox, rb))
+                a.use_tma = 1;
+        }
         a.aligned = ((uintptr_t)j.dR % 4 == 0 && j.pitchR % 4 == 0 && j.frameR % 4 == 0) ? 1 : 0;
         if (a.debug_skip & 4) { uint32_t* gk = nullptr; rc = ensure_gkey(c, dev_index, 4096, &gk); if (rc) return rc; a.gkey = gk; }
         if (a.NC > 1) {

@@ -311,3 +311,25 @@ def test_unaligned_pitch_and_odd_widths(torch_mod, ctx, oracle, variant, B, D):
         L, R = synth_pair(rng, H, W, 1)
         got = dev_run(torch_mod, ctx, L, R, B, D, dict(kernel_variant=variant), pitch_pad=pad)
         assert np.array_equal(got, oracle.frame_box(L, R, B, D)), (H, W, pad, variant, B, D)
+
+
+def test_tma_tile_loader_matches_plain_loader(torch_mod, ctx, oracle):
+    """The warp-specialised kernel loads its tiles with TMA (cp.async.bulk.tensor, hardware zero fill) when base, pitch and
+    frame stride are 16-byte aligned, otherwise with plain loads; both must agree with the oracle at image borders."""
+    import ctypes
+    from despair import _native as N
+    torch = torch_mod
+    rng = np.random.default_rng(33)
+    st = torch.cuda.current_stream().cuda_stream
+    for (W, H, B, D, F) in [(64, 20, 9, 128, 1), (128, 37, 9, 128, 2), (320, 50, 5, 200, 3), (96, 9, 1, 68, 1), (160, 33, 8, 256, 2), (48, 70, 9, 100, 1)]:
+        Ls = rng.integers(0, 256, (F, H, W), dtype=np.uint8); Rs = rng.integers(0, 256, (F, H, W), dtype=np.uint8)
+        dL = torch.from_numpy(Ls).cuda(); dR = torch.from_numpy(Rs).cuda()
+        for no_tma in (0, 1):
+            dO = torch.zeros_like(dL)
+            t = N.Tuning(); t.kernel_variant = 3; t.reserved[2] = no_tma
+            N.check(N.lib().sadgpu_compute_device_batch(ctx._h, 0, F, dL.data_ptr(), W, W * H, dR.data_ptr(), W, W * H, W, H, B, D,
+                                                        0, H, dO.data_ptr(), W, W * H, st, ctypes.byref(t)))
+            torch.cuda.synchronize()
+            got = dO.cpu().numpy()
+            for f in range(F):
+                assert np.array_equal(got[f], oracle.frame_box(Ls[f], Rs[f], B, D)), (W, H, B, D, f, no_tma)
