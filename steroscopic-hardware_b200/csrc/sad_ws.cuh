@@ -33,7 +33,8 @@ template <int HALF> struct WsCfg {
     static constexpr int NTILE = 3;                    // tile buffers: walkers prefetch two batches ahead
     static constexpr int W_CONS = 12;                  // warps 12..22: consumer k = warp-12 (warp 23 idles)
     static constexpr int NT = 768;
-    static constexpr int REGS_LAUNCH = 80, REGS_PROD = 56, REGS_CONS = 104;   // setmaxnreg moves registers inside the CTA's launch allocation
+    static constexpr int REGS_LAUNCH = 80, REGS_PROD = 56, REGS_CONS = 104;
+    static constexpr int REGS_PROD_TMA = 40, REGS_CONS_TMA = 120;           // with TMA the walkers carry no prefetch state   // setmaxnreg moves registers inside the CTA's launch allocation
     static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
     static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;
     static constexpr int RW = NGC - 1 + NWALKW;
@@ -147,7 +148,7 @@ __device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __res
     }
 }
 
-template <int HALF>
+template <int HALF, bool TMA>
 __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid_constant__ FastArgs a)
 {
     using C = WsCfg<HALF>;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid
 
     if (warp < C::W_CONS) {
         // ======================= producer warpgroups (warps 0..11) =======================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(C::REGS_PROD));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(TMA ? C::REGS_PROD_TMA : C::REGS_PROD));
         if (warp == C::W_FIN) {
             // ---- finisher: min over the K partial keys of a pixel, LUT, store (batch it-2) ----
             uint8_t* __restrict__ Og = a.out + (long long)frame * a.frameOut;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid
             // ---- warp 11: TMA tile loader (a.use_tma) — two cp.async.bulk.tensor per batch (raw left rows, aligned right
             //      rows; hardware zero-fill outside the image), completion on an mbarrier, then the left pixels are
             //      replicated into Lrep.  Without TMA this warp idles and the walkers prefetch their own rows. ----
-            if (a.use_tma) {
+            if (TMA) {
                 uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::OFF_MBAR);
                 const uint32_t mbar0 = (uint32_t)__cvta_generic_to_shared(mbar);
                 const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid
 #pragma unroll
                 for (int q = 0; q < NRQ; ++q) { const int j = lane + 32 * q; if (j < C::RWT) Rd[j] = vr[q]; }
             };
-            const bool self_load = !tail && !a.use_tma;
+            const bool self_load = !tail && !TMA;
             if (self_load) {
                 issue(0); commit(0);
                 if (nb > 1) { issue(1); commit(1); }
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid
         }
     } else {
         // ======================= consumer warpgroups (warps 12..23) =======================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(C::REGS_CONS));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(TMA ? C::REGS_CONS_TMA : C::REGS_CONS));
         __syncthreads();
         const int kB = warp - C::W_CONS;
         if (kB < K) {

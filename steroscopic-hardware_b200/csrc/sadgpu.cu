@@ -165,13 +165,14 @@ cudaError_t launch_ws(const FastPlan& p, cudaStream_t s, bool* attr_done)
 {
     using C = WsCfg<HALF>;
     static_assert(C::SMEM <= kSmemBudget, "warp-specialised kernel does not fit shared memory");
-    auto k = sad_ws_kernel<HALF>;
     if (!*attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        cudaError_t e = cudaFuncSetAttribute(sad_ws_kernel<HALF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(sad_ws_kernel<HALF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
         if (e != cudaSuccess) return e;
         *attr_done = true;
     }
-    k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    if (p.a.use_tma) sad_ws_kernel<HALF, true><<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    else             sad_ws_kernel<HALF, false><<<p.grid, C::NT, C::SMEM, s>>>(p.a);
     return cudaGetLastError();
 }
 
