@@ -30,7 +30,7 @@ template <int HALF> struct WsCfg {
     // warp roles (6 warpgroups of 4 warps): producers = warps 0..11, consumers = warps 12..23
     static constexpr int W_TAIL = RB;                  // warp 9: 33rd group, one lane per row
     static constexpr int W_FIN = 10;                   // warp 10: cross-warp min + LUT + store (warp 11 idles)
-    static constexpr int NTILE = 3;                    // tile buffers: walkers prefetch two batches ahead
+    static constexpr int NTILE = 4;                    // tile buffers: tiles are requested three batches ahead, completed two ahead
     static constexpr int W_CONS = 12;                  // warps 12..22: consumer k = warp-12 (warp 23 idles)
     static constexpr int NT = 768;
     static constexpr int REGS_LAUNCH = 80, REGS_PROD = 56, REGS_CONS = 104;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid
                     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
                 }
                 __syncwarp();
-                auto load = [&](int batch) {
+                auto request = [&](int batch) {                 // two bulk tensor copies, completion counted on the buffer's mbarrier
                     const int tb = batch % C::NTILE;
                     const uint32_t bar = mbar0 + 8 * tb;
                     const uint32_t dstR = (uint32_t)__cvta_generic_to_shared(smem + C::OFF_R + tb * C::R_BYTES);
@@ -228,6 +228,10 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid
                         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                                      :: "r"(dstL), "l"(&a.tmapL), "r"(x0 - HALF - C::LSH), "r"(y), "r"(frame), "r"(bar) : "memory");
                     }
+                };
+                auto complete = [&](int batch) {                // wait for the copies of `batch`, then replicate its left pixels
+                    const int tb = batch % C::NTILE;
+                    const uint32_t bar = mbar0 + 8 * tb;
                     // bounded wait on the phase of this buffer's (batch / NTILE)-th use; a stuck copy traps instead of hanging
                     const uint32_t parity = (uint32_t)(batch / C::NTILE) & 1u;
                     uint32_t done = 0;
@@ -242,11 +246,15 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid
                         Ld[idx] = (uint32_t)raw[rb * C::LBOX + C::LSH + i] * 0x01010101u;
                     }
                 };
-                load(0);
-                if (nb > 1) load(1);
+                request(0);
+                if (nb > 1) request(1);
+                if (nb > 2) request(2);
+                complete(0);
+                if (nb > 1) complete(1);
                 __syncthreads();
                 for (int it = 0; it < nb + 2; ++it) {
-                    if (it + 2 < nb) load(it + 2);                 // tile buffer (it+2)%3 was last read in iteration it-1
+                    if (it + 3 < nb) request(it + 3);              // buffer (it+3)%4 was last read in iteration it-1
+                    if (it + 2 < nb) complete(it + 2);             // requested one iteration ago: already landed
                     __syncthreads();
                 }
             } else {

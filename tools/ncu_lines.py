@@ -33,7 +33,7 @@ def main():
     for ln in dis.splitlines():
         m = re.match(r"\s*\.section\s+\.text\.(\S+),", ln)
         if m:
-            inside = all(tok in m.group(1) for tok in re.findall(r"[A-Za-z_]+|\d+", kname.replace("(int)", "")) if tok not in ("void", "int"))
+            inside = all(tok in m.group(1) for tok in re.findall(r"[A-Za-z_]+|\d+", kname.replace("(int)", "").replace("(bool)", "")) if tok not in ("void", "int"))
             continue
         if not inside: continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
