@@ -111,6 +111,9 @@ __device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __res
     const uint32_t keybase = 4u * (uint32_t)(g0 + kB * GT);
     const uint32_t k16 = opaque(a.k65536), mhi = opaque(a.k65536 * 0xFFFFu);
     long long tw = 0, tb = 0, cprev = 0;
+    // unrolled by two so that the ring registers can alternate roles across iterations (the value loaded for row rb is
+    // the "old" value of the next batch): without it every ring update costs a register move
+#pragma unroll 2
     for (int it = 0; it < nb + 2; ++it) {
         if (a.debug_skip & 4) { const volatile uint32_t* vq = pk; tw += (long long)(vq[0] & 0u); }       // forces the deferred barrier wait to complete
         const long long c0 = clock64();
