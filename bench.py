@@ -239,11 +239,11 @@ def main():
         for k in range(F):
             s = k % n_streams
             if tickets[s] is not None:
-                ctx.wait(tickets[s], outs[s])
-            tickets[s] = ctx.submit(pin[k % nuniq][0], pin[k % nuniq][1], B, D, stream=s)
+                ctx.wait(tickets[s])
+            tickets[s] = ctx.submit(pin[k % nuniq][0], pin[k % nuniq][1], B, D, stream=s, out=outs[s])
         for s in range(n_streams):
             if tickets[s] is not None:
-                ctx.wait(tickets[s], outs[s])
+                ctx.wait(tickets[s])
 
     e2e_steps = max(1, min(args.steps, 5))
     step_e2e()
@@ -314,7 +314,7 @@ def main():
             "frames_per_sec": args.steps * F * world / (ms_max * 1e-3), "us_per_frame_per_gpu": us_per_frame,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * W * H * F * world, "d2h_bytes_per_step": W * H * F * world,
                     "frames_per_sec": e2e_steps * F * world / float(t.item()), "parity": e2e_parity,
-                    "how": f"sadgpu_submit/sadgpu_wait, pinned host buffers, {n_streams} streams in flight"},
+                    "how": f"sadgpu_submit_into/sadgpu_wait, pinned host buffers both ways (no host copies), {n_streams} streams in flight"},
             "gpu_launches": args.steps * batches_per_step * launches_per_batch, "frames_per_launch": FB,
             "parity": parity, "plan": despair.plan_describe(W, H, B, D, frames=FB), "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu_baseline}

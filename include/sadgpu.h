@@ -94,6 +94,16 @@ int  sadgpu_submit(sadgpu_ctx *ctx, int stream,
                    uint64_t *ticket);
 int  sadgpu_wait(sadgpu_ctx *ctx, uint64_t ticket, uint8_t *out, int out_stride);
 
+/* sadgpu_submit with the destination named up front: `out` (full-map addressing, rows [y0,y1) written) must lie in
+ * memory from sadgpu_host_alloc, so the D2H copy lands in it directly and sadgpu_wait(ctx, ticket, NULL, 0) only
+ * synchronises — no host-side copy on either side of the frame (the AssembleDisparityMap copy loop,
+ * pkg/despair/sad.go:186-197, disappears; a Go image.Gray can wrap the pinned block).
+ * SADGPU_EINVAL when `out` is not pool memory. */
+int  sadgpu_submit_into(sadgpu_ctx *ctx, int stream,
+                        const uint8_t *left, int left_stride, const uint8_t *right, int right_stride,
+                        int w, int h, int block_size, int max_disparity, int y0, int y1,
+                        uint8_t *out, int out_stride, uint64_t *ticket);
+
 /* One frame split into row bands with a block_size/2 halo over ALL devices of the context
  * (one band per device, streams 0..n_devices-1), host-side gather into out. */
 int  sadgpu_compute_sharded(sadgpu_ctx *ctx,

@@ -509,10 +509,10 @@ int submit_locked(sadgpu_ctx* c, Slot* s, const uint8_t* l, int ls, const uint8_
         if ((rc = upload(c, s, l, ls, s->hL, s->dL, w, ys, ye))) return rc;
         if ((rc = upload(c, s, r, rs, s->hR, s->dR, w, ys, ye))) return rc;
     }
+    s->out_direct = direct_out != nullptr;
     if (y1 > y0) {
         Job j{s->dL, s->pitch, 0, s->dR, s->pitch, 0, s->dOut, s->pitch, 0, 1, w, h, B, D, y0, y1};
         if ((rc = run_job(c, s->dev_index, j, nullptr, s->gkey, s->st))) return rc;
-        s->out_direct = direct_out != nullptr;
         uint8_t* dst = direct_out ? direct_out + (size_t)y0 * direct_stride : s->hOut + (size_t)y0 * s->pitch;
         const size_t dpitch = direct_out ? (size_t)direct_stride : s->pitch;
         if (dpitch == s->pitch && s->pitch == (size_t)w)
@@ -537,8 +537,11 @@ int wait_locked(sadgpu_ctx* c, Slot* s, uint8_t* out, int out_stride)
     if (e != cudaSuccess) return (int)e;
     if (!s->out_direct) {
         if (!out || out_stride < s->w) return SADGPU_EINVAL;
-        for (int y = s->y0; y < s->y1; ++y)
-            memcpy(out + (size_t)y * out_stride, s->hOut + (size_t)y * s->pitch, (size_t)s->w);
+        if ((size_t)out_stride == s->pitch && s->pitch == (size_t)s->w)          // one contiguous block
+            memcpy(out + (size_t)s->y0 * out_stride, s->hOut + (size_t)s->y0 * s->pitch, (size_t)(s->y1 - s->y0) * s->w);
+        else
+            for (int y = s->y0; y < s->y1; ++y)
+                memcpy(out + (size_t)y * out_stride, s->hOut + (size_t)y * s->pitch, (size_t)s->w);
     }
     return SADGPU_OK;
 }
@@ -652,6 +655,25 @@ int sadgpu_submit(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, const uin
     std::lock_guard<std::mutex> g(s->mu);
     if (s->busy) return SADGPU_EBUSY;
     rc = submit_locked(c, s, l, ls, r, rs, w, h, B, D, y0, y1, nullptr, 0);
+    if (rc) { cudaStreamSynchronize(s->st); s->busy = false; return rc; }
+    s->seq++;
+    *ticket = (s->seq << 16) | (uint64_t)stream;
+    return SADGPU_OK;
+}
+
+int sadgpu_submit_into(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, const uint8_t* r, int rs,
+                       int w, int h, int B, int D, int y0, int y1, uint8_t* out, int out_stride, uint64_t* ticket)
+{
+    int rc = check_io(c, stream, l, ls, r, rs, w, h);
+    if (rc) return rc;
+    if (!ticket || !out || out_stride < w) return SADGPU_EINVAL;
+    if ((rc = validate(w, h, B, D, y0, y1))) return rc;
+    // the destination is retained until sadgpu_wait: only the context's own pinned memory qualifies (cgo pointer rule)
+    if (y1 > y0 && !in_pool(c, out + (size_t)y0 * out_stride, (size_t)(y1 - y0 - 1) * out_stride + w)) return SADGPU_EINVAL;
+    Slot* s = c->slots[stream];
+    std::lock_guard<std::mutex> g(s->mu);
+    if (s->busy) return SADGPU_EBUSY;
+    rc = submit_locked(c, s, l, ls, r, rs, w, h, B, D, y0, y1, out, out_stride);
     if (rc) { cudaStreamSynchronize(s->st); s->busy = false; return rc; }
     s->seq++;
     *ticket = (s->seq << 16) | (uint64_t)stream;

@@ -57,17 +57,27 @@ class Context:
                                         w, h, block_size, max_disparity, y0, y1, out.ctypes.data, out.strides[0]))
         return out
 
-    def submit(self, left, right, block_size, max_disparity, y0=0, y1=None, stream=0):
+    def submit(self, left, right, block_size, max_disparity, y0=0, y1=None, stream=0, out=None):
+        """Enqueue one frame.  With `out` (an array from host_array) the result is written there by the D2H copy
+        itself (sadgpu_submit_into) and wait(ticket) needs no destination."""
         l = _u8_2d(left, "left"); r = _u8_2d(right, "right")
         h, w = l.shape
         y1 = h if y1 is None else y1
         t = ctypes.c_uint64()
-        N.check(self._L.sadgpu_submit(self._h, stream, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
-                                       w, h, block_size, max_disparity, y0, y1, ctypes.byref(t)))
+        if out is None:
+            N.check(self._L.sadgpu_submit(self._h, stream, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
+                                           w, h, block_size, max_disparity, y0, y1, ctypes.byref(t)))
+        else:
+            N.check(self._L.sadgpu_submit_into(self._h, stream, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
+                                                w, h, block_size, max_disparity, y0, y1, out.ctypes.data, out.strides[0],
+                                                ctypes.byref(t)))
         return t.value
 
-    def wait(self, ticket, out):
-        N.check(self._L.sadgpu_wait(self._h, ticket, out.ctypes.data, out.strides[0]))
+    def wait(self, ticket, out=None):
+        if out is None:
+            N.check(self._L.sadgpu_wait(self._h, ticket, None, 0))
+        else:
+            N.check(self._L.sadgpu_wait(self._h, ticket, out.ctypes.data, out.strides[0]))
         return out
 
     def compute_sharded(self, left, right, block_size, max_disparity, out=None):

@@ -234,6 +234,42 @@ def test_pinned_pool_zero_copy_path(ctx, oracle):
     assert np.array_equal(pO, oracle.frame_box(L, R, 7, 32))
 
 
+def test_submit_into_pinned_destination(ctx, oracle):
+    """sadgpu_submit_into: the D2H copy lands in the caller's pinned map, wait() copies nothing; row ranges assemble."""
+    import despair
+    rng = np.random.default_rng(11)
+    frames = [synth_pair(rng, 96, 200, 1) for _ in range(6)]        # width 200: pitch == w (multiple of 4)
+    pins = [ctx.host_pair(96, 200) for _ in frames]
+    outs = [ctx.host_array((96, 200)) for _ in frames]
+    for (pl, pr), (L, R), o in zip(pins, frames, outs):
+        pl[:] = L; pr[:] = R; o[:] = 7
+    tickets = {}
+    for k in range(len(frames)):
+        s = k % 4
+        if s in tickets:
+            ctx.wait(tickets.pop(s))
+        tickets[s] = ctx.submit(pins[k][0], pins[k][1], 9, 64, stream=s, out=outs[k])
+    for t in tickets.values():
+        ctx.wait(t)
+    for o, (L, R) in zip(outs, frames):
+        assert np.array_equal(o, oracle.frame_box(L, R, 9, 64))
+    # two disjoint row ranges of one map, odd width (2-D copies), rows outside stay untouched
+    L, R = synth_pair(rng, 64, 101, 0)
+    o = ctx.host_array((64, 101)); o[:] = 9
+    t0 = ctx.submit(L, R, 5, 32, y0=0, y1=30, stream=0, out=o)
+    t1 = ctx.submit(L, R, 5, 32, y0=30, y1=60, stream=1, out=o)
+    ctx.wait(t0); ctx.wait(t1)
+    exp = oracle.frame_box(L, R, 5, 32)
+    assert np.array_equal(o[:60], exp[:60]) and (o[60:] == 9).all()
+    with pytest.raises(despair.SadGpuError) as e:                   # pageable destination: refused, nothing is retained
+        ctx.submit(L, R, 5, 32, stream=0, out=np.zeros((64, 101), np.uint8))
+    assert e.value.code == -1
+    t = ctx.submit(L, R, 5, 32, stream=0)
+    with pytest.raises(despair.SadGpuError) as e:                   # plain submit needs a destination at wait
+        ctx.wait(t)
+    assert e.value.code == -1
+
+
 def test_error_codes(ctx):
     import despair
     L = np.zeros((10, 10), np.uint8)
