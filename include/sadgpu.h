@@ -62,7 +62,9 @@ typedef struct sadgpu_tuning {
     int groups_per_chunk;   /* disparity groups (4 disparities each) per CTA chunk     */
     int kernel_variant;     /* 0 = auto, 1 = generic (any block size), 2 = register-ring fast path (block_size <= 15),
                                3 = warp-specialised fast path (block_size <= 9, max_disparity >= 68),
-                               4 = large-window kernel (block_size 16..31) */
+                               4 = large-window kernel (block_size 16..31),
+                               5 = vertical-first mbarrier-pipelined kernel (block_size 10..31),
+                               6 = H-ring mbarrier-pipelined kernel (block_size 10..15; the default there for max_disparity >= 72) */
     int reserved[4];        /* [0]: frames per launch (sadgpu_plan_describe only); [1]: developer flags (role idling, cycle counters);
                                [2] = 1: do not use TMA tile loads in the warp-specialised kernel */
 } sadgpu_tuning;

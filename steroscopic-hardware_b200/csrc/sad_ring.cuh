@@ -1,0 +1,408 @@
+// sad_ring.cuh — warp-specialised kernel for the mid-size windows (block_size 11..15, h = 5..7) where the 2h+1
+// previous rows of horizontal sums neither fit a register ring (sad_ws.cuh) nor need 32-bit arithmetic.
+//
+// Same arithmetic and the same two passes as sad_ws.cuh (pkg/despair/sad.go:55-95, :205-244 through the separable box
+// filter): row walkers produce the horizontal window sums H(row, group, column), column consumers keep the vertical
+// running sums V += H(y+h) - H(y-h-1) and the key-min argmin.  The difference is where the leaving row comes from: all
+// H rows of the window live in a SHARED-MEMORY RING of 2h+2+NWK rows (24 rows x 8.5 KB at h = 7) and the consumers
+// read the entering and the leaving row (two LDS.64 per 4 candidates).  A ring that deep leaves no room for double
+// buffering by batches, so every hand-over is row-granular and goes through an mbarrier:
+//   loaders --tile_full--> walkers / tail walker --h_full--> consumers --pk_full--> finisher
+//           <--tile_empty--                      <--h_empty--          <--pk_empty--
+// 24 warps with fixed roles: 8 walkers (one row each, lanes = 32 disparity groups), 1 tail walker (33rd group of four
+// rows, lanes = row x column segment), 11 consumers (3 groups x 32 columns, four rows per step), 1 finisher, 2 loaders.
+// Candidates the reference never evaluates (d > min(D, X-h)) lose through per-thread key constants (multiplier 0 /
+// all-ones addend): no instruction is spent on them.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "sad_fast.cuh"
+
+namespace sadgpu {
+
+template <int HALF> struct RingCfg {
+    static_assert(HALF >= 1 && HALF <= 7, "ring kernel: 16-bit window sums, block_size <= 15");
+    static constexpr int WIN = 2 * HALF + 1;
+    static constexpr int TW = 32, TWP = 33;
+    static constexpr int NSTEP = TW + 2 * HALF;
+    static constexpr int LW = (NSTEP + 3) & ~3;
+    static constexpr int NGC = 33, GT = 3, K = 11;
+    static constexpr int NWK = 4;                                   // walker warps = rows in flight (window + consumed burst + written burst <= NRH)
+    // Ring sizes are multiples of the number of warps that take turns on them (8 walkers; 2 loaders x 4 rows), so that a
+    // slot is always produced by the same warp: a parity wait is only sound for a waiter that has seen every phase.
+    static constexpr int NRH = 24;                                  // H ring rows: 2h+2 of the window + two bursts of NWK rows
+    static constexpr int TR = 16;                                   // pixel-tile ring rows
+    static constexpr int RT = 4, SEGW = 4;                          // tail walker: rows per step, columns per lane
+    static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
+    static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;
+    static constexpr int RW = NGC - 1 + NWALKW;                     // words per aligned-R tile row
+    static constexpr int HROW = NGC * TWP;                          // uint2 per H row
+    static constexpr int NT = 768;
+    // warp roles; SM sub-partition = warp % 4
+    static constexpr int W_CONS = 8, W_TAIL = 19, W_FIN = 20, W_LD0 = 21, W_LD1 = 22, W_FIN2 = 23;
+    static constexpr int H_BYTES = NRH * HROW * 8;
+    static constexpr int OFF_L = ((H_BYTES + 15) / 16) * 16;
+    static constexpr int OFF_R = OFF_L + TR * LW * 4;
+    static constexpr int OFF_PK = OFF_R + TR * RW * 4;              // [2][4][K][TW]
+    static constexpr int OFF_LUT = OFF_PK + 2 * 4 * K * TW * 4;
+    static constexpr int OFF_BAR = ((OFF_LUT + 1040 + 7) / 8) * 8;
+    static constexpr int WSPLIT = 2;                                // walker warps per row (column halves)
+    static constexpr int NB = NRH / NWK;                            // bursts in the H ring
+    static constexpr int OB = (WIN + NWK - 1) / NWK;                // a burst has left every window OB bursts later
+    static constexpr int OB0 = (2 * HALF) / NWK;                    // first burst that holds an output row
+    static constexpr int NBAR = 2 * NB + 2 * TR + 4;
+    static constexpr int SMEM = OFF_BAR + NBAR * 8;
+    static_assert(GT * K == NGC && RT * (TW / SEGW) == 32 && W_CONS + K == W_TAIL, "roles");
+    static_assert(NWK == 4 && NWK * WSPLIT <= W_CONS && RT == NWK && NRH % NWK == 0 && TR % (2 * NWK) == 0, "every ring slot belongs to one producer warp");
+    static_assert(NB >= OB + 2, "ring: window bursts + the burst being consumed + the burst being written");
+};
+
+__device__ __forceinline__ void ring_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+// Bounded wait (try_wait suspends the warp in hardware): a protocol error traps instead of hanging the GPU.
+#ifndef RING_SLEEP_NS
+#define RING_SLEEP_NS 0          // back-off between two failed try_wait probes (0 = probe again at once)
+#endif
+#define RING_STR2(x) #x
+#define RING_STR(x) RING_STR2(x)
+__device__ __forceinline__ void ring_wait_(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .u32 n;\n"
+        "mov.u32 n, 0;\n"
+        "RING_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "@p bra RING_WAIT_DONE;\n"
+#if RING_SLEEP_NS > 0
+        "nanosleep.u32 " RING_STR(RING_SLEEP_NS) ";\n"
+#endif
+        "add.u32 n, n, 1;\n"
+        "setp.lt.u32 p, n, 4000000;\n"
+        "@p bra RING_WAIT_LOOP;\n"
+        "RING_WAIT_DONE:\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok) __trap();
+}
+
+#ifdef RING_PROFILE       // developer build: per-warp cycles spent waiting on each barrier family, written for one CTA
+#define RING_WAIT(bar, parity, slot) do { const long long c0_ = clock64(); ring_wait_(bar, parity); wt[slot] += clock64() - c0_; } while (0)
+#define RING_PROF_BEGIN long long wt[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long c00_ = clock64()
+#define RING_PROF_END(dbg) do { if (dbg && (threadIdx.x & 31) == 0) { wt[7] = clock64() - c00_; \
+    for (int i_ = 0; i_ < 8; ++i_) dbg[(threadIdx.x >> 5) * 8 + i_] = (uint32_t)(wt[i_] >> 4); } } while (0)
+#else
+#define RING_WAIT(bar, parity, slot) ring_wait_(bar, parity)
+#define RING_PROF_BEGIN do {} while (0)
+#define RING_PROF_END(dbg) do {} while (0)
+#endif
+
+// One walk of NOUT outputs (NOUT + 2h steps, fully unrolled): Lr / Rr / Hout point at the first step's operands.
+template <int HALF, int NOUT, bool EDGE>
+__device__ __forceinline__ void ring_walk(const uint32_t* __restrict__ Lr, const uint32_t* __restrict__ Rr,
+                                          uint2* __restrict__ Hout, int nvalid, bool store)
+{
+    using T = RingCfg<HALF>;
+    constexpr int NS = NOUT + 2 * HALF;
+    uint32_t e[NS], o[NS];
+    uint32_t hE = 0, hO = 0, w0 = 0, w1 = 0;
+    uint4 lv = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        if ((i & 3) == 0) lv = *reinterpret_cast<const uint4*>(Lr + i);
+        const int bi = i + T::OFF;
+        if (i == 0) { w0 = Rr[bi >> 2]; w1 = Rr[(bi >> 2) + 1]; }
+        else if ((bi & 3) == 0) { w0 = w1; w1 = Rr[(bi >> 2) + 1]; }
+        const uint32_t lw = (i & 3) == 0 ? lv.x : (i & 3) == 1 ? lv.y : (i & 3) == 2 ? lv.z : lv.w;
+        const uint32_t rw = (bi & 3) == 0 ? w0 : __funnelshift_r(w0, w1, 8 * (bi & 3));
+        uint32_t ad = __vabsdiffu4(lw, rw);
+        if (EDGE) ad = (i < nvalid) ? ad : 0u;                  // columns x >= W contribute nothing
+        e[i] = __byte_perm(ad, 0u, 0x4240);                     // (d=4g+3 | d=4g+1 << 16)
+        o[i] = __byte_perm(ad, 0u, 0x4341);                     // (d=4g+2 | d=4g   << 16)
+        if (i >= T::WIN) { hE = hE + e[i] - e[i - T::WIN]; hO = hO + o[i] - o[i - T::WIN]; }
+        else             { hE += e[i]; hO += o[i]; }
+        if (i >= 2 * HALF && store) Hout[i - 2 * HALF] = make_uint2(hE, hO);
+    }
+}
+
+template <int HALF>
+__global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __grid_constant__ FastArgs a)
+{
+    using C = RingCfg<HALF>;
+    constexpr int WIN = C::WIN, TW = C::TW, TWP = C::TWP, NGC = C::NGC, GT = C::GT, K = C::K, NRH = C::NRH, TR = C::TR;
+    constexpr int HROW = C::HROW, LW = C::LW, RW = C::RW, NWK = C::NWK, NB = C::NB, OB = C::OB, OB0 = C::OB0;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint2* Hs = reinterpret_cast<uint2*>(smem);                                   // [NRH][NGC][TWP]
+    uint32_t* Lrep = reinterpret_cast<uint32_t*>(smem + C::OFF_L);               // [TR][LW]
+    uint32_t* Ral = reinterpret_cast<uint32_t*>(smem + C::OFF_R);                // [TR][RW]
+    uint32_t* pk = reinterpret_cast<uint32_t*>(smem + C::OFF_PK);                // [2][4][K][TW]
+    uint8_t* lut = smem + C::OFF_LUT;
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(smem + C::OFF_BAR);
+    const uint32_t hfull = bar0, hempty = bar0 + 8 * NB, tfull = bar0 + 16 * NB, tempty = tfull + 8 * TR;
+    const uint32_t pkfull = tempty + 8 * TR, pkempty = pkfull + 16;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int frame = blockIdx.z / a.NC, chunk = blockIdx.z - frame * a.NC;
+    const int x0 = blockIdx.x * TW;
+    const int yb0 = a.y0 + blockIdx.y * a.BH;
+    const int yb1 = min(a.y1, yb0 + a.BH);
+    if (yb0 >= yb1) return;
+    const int g0 = chunk * NGC;
+    const int bhc = yb1 - yb0, nin = bhc + 2 * HALF;          // output rows / H rows of this band (H row r = image row yb0-h+r)
+    const int nvalid = a.W - (x0 - HALF);
+    const int nbur = (nin + NWK - 1) / NWK;                   // bursts of NWK rows
+
+    for (int d = tid; d < 1040; d += C::NT) lut[d] = d <= a.D ? (uint8_t)((d * 255) / a.D) : 0;
+    if (tid == 0) {
+        for (int i = 0; i < NB; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(hfull + 8 * i), "n"(NWK * C::WSPLIT + 1));  // walkers + tail walker
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(hempty + 8 * i), "n"(K));
+        }
+        for (int i = 0; i < TR; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tfull + 8 * i));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tempty + 8 * i), "n"(C::WSPLIT + 1));   // walkers + tail walker
+        }
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(pkfull + 8 * i), "n"(K));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(pkempty + 8 * i));             // two finishers
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint32_t* dbg = ((a.debug_skip & 4) && blockIdx.x == 7 && blockIdx.y == 0 && blockIdx.z == 0) ? a.gkey : nullptr;
+    (void)dbg;
+    RING_PROF_BEGIN;
+    if (warp < NWK * C::WSPLIT) {
+        // ---- walkers: warps w and w+NWK walk the two 16-column halves of row w of every burst for groups 0..31
+        //      (lanes = groups); the second half re-warms its window over 2h columns ----
+        const int wr = warp % NWK, wh = warp / NWK;
+        constexpr int HW = TW / C::WSPLIT;
+        for (int bi = 0; bi < nbur; ++bi) {
+            const int r = NWK * bi + wr, bs = bi % NB;
+            if (r < nin) {
+                const int ts = r % TR;
+                RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
+                if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
+                const uint32_t* Lr = Lrep + ts * LW + HW * wh;
+                const uint32_t* Rr = Ral + ts * RW + (NGC - 1 - lane) + (HW / 4) * wh;
+                uint2* Hout = Hs + (bs * NWK + wr) * HROW + lane * TWP + HW * wh;
+                if (nvalid >= C::NSTEP) ring_walk<HALF, HW, false>(Lr, Rr, Hout, nvalid - HW * wh, true);
+                else                    ring_walk<HALF, HW, true>(Lr, Rr, Hout, nvalid - HW * wh, true);
+                __syncwarp();
+                if (lane == 0) ring_arrive(tempty + 8 * ts);
+            }
+            if (lane == 0) ring_arrive(hfull + 8 * bs);
+        }
+    } else if (warp == C::W_TAIL) {
+        // ---- tail walker: group NGC-1 of the four rows of a burst; lane = (row j, segment s of SEGW columns) ----
+        const int j = lane >> 3, s = lane & 7;
+        for (int bi = 0; bi < nbur; ++bi) {
+            const int r = NWK * bi + j, bs = bi % NB;
+            const bool act = r < nin;
+            const int ts = r % TR;
+            if (act) RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
+            if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
+            __syncwarp();
+            const uint32_t* Lr = Lrep + ts * LW + C::SEGW * s;
+            const uint32_t* Rr = Ral + ts * RW + s;
+            uint2* Hout = Hs + (bs * NWK + j) * HROW + (NGC - 1) * TWP + C::SEGW * s;
+            if (nvalid >= C::NSTEP) ring_walk<HALF, C::SEGW, false>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
+            else                    ring_walk<HALF, C::SEGW, true>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
+            __syncwarp();
+            if (act && s == 0) ring_arrive(tempty + 8 * ts);
+            if (lane == 0) ring_arrive(hfull + 8 * bs);
+        }
+    } else if (warp == C::W_LD0 || warp == C::W_LD1) {
+        // ---- loaders: rows in groups of four, alternating between the two warps; replicated left pixels and aligned
+        //      right words of one row per tile slot ----
+        const int li = warp == C::W_LD0 ? 0 : 1;
+        const uint8_t* __restrict__ Lg = a.L + (long long)frame * a.frameL;
+        const uint8_t* __restrict__ Rg = a.R + (long long)frame * a.frameR;
+        const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;     // image column of R tile word 0 (multiple of 4)
+        constexpr int NLQ = (LW + 31) / 32, NRQ = (RW + 31) / 32;
+        int lx[NLQ], rx[NRQ], rmode[NRQ];
+#pragma unroll
+        for (int q = 0; q < NLQ; ++q) {
+            const int i = lane + 32 * q, x = x0 - HALF + i;
+            lx[q] = (i < LW && (unsigned)x < (unsigned)a.W) ? x : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < NRQ; ++q) {
+            const int jw = lane + 32 * q, x = xr0 + 4 * jw;
+            const bool in = jw < RW && x + 3 >= 0 && x < a.W;
+            rx[q] = x;
+            rmode[q] = !in ? 0 : (a.aligned && x >= 0 && x + 3 < a.W) ? 1 : 2;
+        }
+        constexpr int GRP = 4;
+        // interior strips (every tile column inside the image, 4-byte aligned rows): no per-lane tests in the load loop
+        const bool interior = a.aligned && x0 - HALF >= 0 && x0 - HALF + LW <= a.W && xr0 >= 0 && xr0 + 4 * RW <= a.W;
+        const int li0 = min(lane, LW - 1), li1 = min(lane + 32, LW - 1);          // clamped: the surplus lanes reload a valid pixel
+        const int rj0 = min(lane, RW - 1), rj1 = min(lane + 32, RW - 1);
+        static_assert(NLQ == 2 && NRQ == 2, "two tile words per lane");
+        auto issue = [&](int t, uint32_t (&vl)[GRP][NLQ], uint32_t (&vr)[GRP][NRQ]) {      // global loads of the burst starting at row t
+#pragma unroll
+            for (int u = 0; u < GRP; ++u) {
+                const int y = yb0 - HALF + t + u;
+                const bool yin = t + u < nin && (unsigned)y < (unsigned)a.H;
+                const uint8_t* pl = Lg + (size_t)(yin ? y : 0) * a.pitchL;
+                const uint8_t* pr = Rg + (size_t)(yin ? y : 0) * a.pitchR;
+                if (interior) {
+                    vl[u][0] = vl[u][1] = vr[u][0] = vr[u][1] = 0;
+                    if (yin) {
+                        vl[u][0] = pl[x0 - HALF + li0]; vl[u][1] = pl[x0 - HALF + li1];
+                        vr[u][0] = *reinterpret_cast<const uint32_t*>(pr + xr0 + 4 * rj0);
+                        vr[u][1] = *reinterpret_cast<const uint32_t*>(pr + xr0 + 4 * rj1);
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int q = 0; q < NLQ; ++q) { vl[u][q] = 0; if (yin && lx[q] >= 0) vl[u][q] = pl[lx[q]]; }
+#pragma unroll
+                for (int q = 0; q < NRQ; ++q) {
+                    uint32_t v = 0;
+                    if (yin && rmode[q] == 1) v = *reinterpret_cast<const uint32_t*>(pr + rx[q]);
+                    else if (yin && rmode[q] == 2) {
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if ((unsigned)(rx[q] + b) < (unsigned)a.W) v |= (uint32_t)pr[rx[q] + b] << (8 * b);
+                    }
+                    vr[u][q] = v;
+                }
+            }
+        };
+        auto commit = [&](int t, uint32_t (&vl)[GRP][NLQ], uint32_t (&vr)[GRP][NRQ]) {     // registers -> tile slots, one arrive per row
+#pragma unroll
+            for (int u = 0; u < GRP; ++u) {
+                const int r = t + u;
+                if (r >= nin) break;
+                const int ts = r % TR;
+                if (r >= TR) RING_WAIT(tempty + 8 * ts, (uint32_t)(r / TR - 1) & 1u, 2);
+                uint32_t* Ld = Lrep + ts * LW;
+                uint32_t* Rd = Ral + ts * RW;
+#pragma unroll
+                for (int q = 0; q < NLQ; ++q) { const int i = lane + 32 * q; if (i < LW) Ld[i] = vl[u][q] * 0x01010101u; }
+#pragma unroll
+                for (int q = 0; q < NRQ; ++q) { const int jw = lane + 32 * q; if (jw < RW) Rd[jw] = vr[u][q]; }
+                __syncwarp();
+                if (lane == 0) ring_arrive(tfull + 8 * ts);
+            }
+        };
+        // two register sets: the loads of this warp's next burst are in flight while the current one waits for its slots
+        uint32_t vlA[GRP][NLQ], vrA[GRP][NRQ], vlB[GRP][NLQ], vrB[GRP][NRQ];
+        int t = GRP * li;
+        if (t < nin) issue(t, vlA, vrA);
+        for (; t < nin; t += 4 * GRP) {
+            const bool more = t + 2 * GRP < nin;
+            if (more) issue(t + 2 * GRP, vlB, vrB);
+            commit(t, vlA, vrA);
+            if (more) {
+                if (t + 4 * GRP < nin) issue(t + 4 * GRP, vlA, vrA);
+                commit(t + 2 * GRP, vlB, vrB);
+            }
+        }
+    } else if (warp == C::W_FIN || warp == C::W_FIN2) {
+        // ---- finishers: min over the K partial keys of a pixel, LUT, store; each warp takes two rows of every burst ----
+        const int fh = warp == C::W_FIN ? 0 : 2;
+        uint8_t* __restrict__ Og = a.out + (long long)frame * a.frameOut;
+        const int x = x0 + lane;
+        for (int bi = OB0, ob = 0; bi < nbur; ++bi, ++ob) {
+            RING_WAIT(pkfull + 8 * (ob & 1), (uint32_t)(ob >> 1) & 1u, 4);
+            const uint32_t* pkb = pk + (ob & 1) * 4 * K * TW + lane;
+#pragma unroll
+            for (int uu = 0; uu < 2; ++uu) {
+                const int u = fh + uu;
+                const int k = NWK * bi + u - 2 * HALF, y = yb0 + k;
+                if (k < 0 || k >= bhc || x >= a.W) continue;
+                uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+                for (int kk = 0; kk < K; ++kk) best = min(best, pkb[(u * K + kk) * TW]);
+                if (x < HALF) best = 0;                      // sad.go:212-218: both windows clamp, d = 0 wins
+                if (a.NC == 1) Og[(size_t)y * a.pitchOut + x] = lut[best & 0xFFFFu];
+                else atomicMin(a.gkey + ((size_t)frame * a.H + y) * a.W + x, ((best >> 16) << 9) | (best & 511u));
+            }
+            __syncwarp();
+            if (lane == 0) ring_arrive(pkempty + 8 * (ob & 1));
+        }
+    } else if (warp >= C::W_CONS && warp < C::W_CONS + K) {
+        // ---- consumers: warp k owns groups 3k..3k+2 of 32 columns (lanes = columns); vertical running sums from the
+        //      entering and the leaving H row, keys, partial best -> pk; one barrier wait per burst of four rows ----
+        const int kB = warp - C::W_CONS;
+        const int xB = x0 + lane;
+        const int dmax = min(a.D, xB - HALF);               // largest evaluated disparity of this column (sad.go:64-67, :212-218)
+        const uint32_t k16 = opaque(a.k65536);
+        uint32_t mE[GT], aE[GT], nE[GT], oE[GT], mO[GT], aO[GT], nO[GT], oO[GT];
+        uint32_t VE[GT], VO[GT];
+#pragma unroll
+        for (int j = 0; j < GT; ++j) {
+            const int dG = 4 * (g0 + kB * GT + j);
+            const bool v3 = dG + 3 <= dmax, v1 = dG + 1 <= dmax, v2 = dG + 2 <= dmax, v0 = dG <= dmax;
+            mE[j] = v3 ? k16 : 0u; aE[j] = v3 ? (uint32_t)(dG + 3) : 0xFFFFFFFFu;
+            nE[j] = v1 ? 0xFFFF0000u : 0u; oE[j] = v1 ? (uint32_t)(dG + 1) : 0xFFFFFFFFu;
+            mO[j] = v2 ? k16 : 0u; aO[j] = v2 ? (uint32_t)(dG + 2) : 0xFFFFFFFFu;
+            nO[j] = v0 ? 0xFFFF0000u : 0u; oO[j] = v0 ? (uint32_t)dG : 0xFFFFFFFFu;
+            VE[j] = 0; VO[j] = 0;
+        }
+        const uint2* Hk = Hs + (kB * GT) * TWP + lane;
+        auto keys = [&]() {
+            uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+            for (int j = 0; j < GT; ++j) {
+                const uint32_t kEl = VE[j] * mE[j] + aE[j], kEh = (VE[j] & nE[j]) | oE[j];
+                const uint32_t kOl = VO[j] * mO[j] + aO[j], kOh = (VO[j] & nO[j]) | oO[j];
+                best = min(best, min(kEl, kEh));
+                best = min(best, min(kOl, kOh));
+            }
+            return best;
+        };
+        for (int bi = 0; bi < nbur; ++bi) {
+            const int bs = bi % NB, ob = bi - OB0;
+            RING_WAIT(hfull + 8 * bs, (uint32_t)(bi / NB) & 1u, 3);
+            if (ob >= 2) RING_WAIT(pkempty + 8 * (ob & 1), (uint32_t)((ob >> 1) - 1) & 1u, 5);
+            uint32_t* pkb = pk + ((ob & 1) * 4 * K + kB) * TW + lane;
+            const int sn0 = bs * NWK;
+            if (NWK * bi >= WIN && NWK * bi + 3 < nin) {
+                // steady state: every row of the burst has a leaving row and an output row
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    int so = sn0 + u - WIN; if (so < 0) so += NRH;
+                    const uint2* Hn = Hk + (sn0 + u) * HROW;
+                    const uint2* Ho = Hk + so * HROW;
+#pragma unroll
+                    for (int j = 0; j < GT; ++j) {
+                        const uint2 n = Hn[j * TWP], o = Ho[j * TWP];
+                        VE[j] = VE[j] + n.x - o.x; VO[j] = VO[j] + n.y - o.y;
+                    }
+                    pkb[u * K * TW] = keys();
+                }
+            } else {
+                for (int u = 0; u < 4; ++u) {
+                    const int r = NWK * bi + u;
+                    if (r >= nin) break;
+                    const uint2* Hn = Hk + (sn0 + u) * HROW;
+#pragma unroll
+                    for (int j = 0; j < GT; ++j) { const uint2 n = Hn[j * TWP]; VE[j] += n.x; VO[j] += n.y; }
+                    if (r >= WIN) {
+                        int so = sn0 + u - WIN; if (so < 0) so += NRH;
+                        const uint2* Ho = Hk + so * HROW;
+#pragma unroll
+                        for (int j = 0; j < GT; ++j) { const uint2 o = Ho[j * TWP]; VE[j] -= o.x; VO[j] -= o.y; }
+                    }
+                    if (r >= 2 * HALF) pkb[u * K * TW] = keys();
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (bi >= OB) ring_arrive(hempty + 8 * ((bi - OB) % NB));       // burst bi-OB has left every window
+                if (ob >= 0) ring_arrive(pkfull + 8 * (ob & 1));
+            }
+        }
+    }
+    RING_PROF_END(dbg);
+}
+
+}  // namespace sadgpu

@@ -6,6 +6,8 @@
 #include "sad_fast.cuh"
 #include "sad_ws.cuh"
 #include "sad_wide.cuh"
+#include "sad_vh.cuh"
+#include "sad_ring.cuh"
 #include "gray_kernels.cuh"
 
 #include <algorithm>
@@ -24,6 +26,16 @@ constexpr int kSmemBudget = 232448;      // 227 KB opt-in dynamic shared memory 
 constexpr int kGT = 5;                   // disparity groups per phase-B thread
 constexpr int kMaxThreadsPerColumn = 4;  // K: phase-B threads per pixel column
 constexpr int kMaxDevices = 64;
+
+// Developer builds (-DSADGPU_DEV_H0=7 -DSADGPU_DEV_H1=15) instantiate the kernels of two half-windows only: seconds, not minutes.
+constexpr bool dev_on(int half)
+{
+#ifdef SADGPU_DEV_H0
+    return half == SADGPU_DEV_H0 || half == SADGPU_DEV_H1;
+#else
+    (void)half; return true;
+#endif
+}
 
 struct Plan {
     SadArgs a;
@@ -126,11 +138,15 @@ cudaError_t launch_generic(const Plan& p, cudaStream_t s, bool* attr_done)
 }
 
 typedef cudaError_t (*launch_fn)(const Plan&, cudaStream_t, bool*);
+template <int HALF> constexpr launch_fn generic_entry()
+{
+    if constexpr (dev_on(HALF)) return launch_generic<HALF>; else return nullptr;
+}
 const launch_fn kLaunchGeneric[16] = {
-    launch_generic<0>, launch_generic<1>, launch_generic<2>, launch_generic<3>,
-    launch_generic<4>, launch_generic<5>, launch_generic<6>, launch_generic<7>,
-    launch_generic<8>, launch_generic<9>, launch_generic<10>, launch_generic<11>,
-    launch_generic<12>, launch_generic<13>, launch_generic<14>, launch_generic<15>};
+    generic_entry<0>(), generic_entry<1>(), generic_entry<2>(), generic_entry<3>(),
+    generic_entry<4>(), generic_entry<5>(), generic_entry<6>(), generic_entry<7>(),
+    generic_entry<8>(), generic_entry<9>(), generic_entry<10>(), generic_entry<11>(),
+    generic_entry<12>(), generic_entry<13>(), generic_entry<14>(), generic_entry<15>()};
 
 
 // ---------------------------------------------------------------------------------------
@@ -141,7 +157,7 @@ struct FastPlan {
     dim3 grid;
     int nthreads;
     size_t smem;
-    int half, ngc, rb;
+    int half, ngc, rb, tw;
     int launches;
 };
 
@@ -191,11 +207,62 @@ cudaError_t launch_wide(const FastPlan& p, cudaStream_t s, bool* attr_done)
     return cudaGetLastError();
 }
 
+template <int HALF>
+cudaError_t launch_vh(const FastPlan& p, cudaStream_t s, bool* attr_done)
+{
+    using C = VhCfg<HALF>;
+    static_assert(C::SMEM <= kSmemBudget, "vertical-first kernel does not fit shared memory");
+    auto k = sad_vh_kernel<HALF>;
+    if (!*attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return e;
+        *attr_done = true;
+    }
+    k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    return cudaGetLastError();
+}
+
+template <int HALF>
+cudaError_t launch_ring(const FastPlan& p, cudaStream_t s, bool* attr_done)
+{
+    using C = RingCfg<HALF>;
+    static_assert(C::SMEM <= kSmemBudget, "ring kernel does not fit shared memory");
+    auto k = sad_ring_kernel<HALF>;
+    if (!*attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
+        if (e != cudaSuccess) return e;
+        *attr_done = true;
+    }
+    k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    return cudaGetLastError();
+}
+
 typedef cudaError_t (*fast_fn)(const FastPlan&, cudaStream_t, bool*);
 struct FastEntry { fast_fn fn; int nt, smem, rb; };
 template <int HALF, int NGC> constexpr FastEntry fast_entry()
 {
-    return FastEntry{launch_fast<HALF, NGC>, FastCfg<HALF, NGC>::NT, FastCfg<HALF, NGC>::SMEM, FastCfg<HALF, NGC>::RB};
+    if constexpr (dev_on(HALF)) return FastEntry{launch_fast<HALF, NGC>, FastCfg<HALF, NGC>::NT, FastCfg<HALF, NGC>::SMEM, FastCfg<HALF, NGC>::RB};
+    else return FastEntry{nullptr, FastCfg<HALF, NGC>::NT, FastCfg<HALF, NGC>::SMEM, FastCfg<HALF, NGC>::RB};
+}
+template <int HALF> constexpr FastEntry ws_entry()
+{
+    if constexpr (dev_on(HALF)) return FastEntry{launch_ws<HALF>, WsCfg<HALF>::NT, WsCfg<HALF>::SMEM, WsCfg<HALF>::RB};
+    else return FastEntry{nullptr, WsCfg<HALF>::NT, WsCfg<HALF>::SMEM, WsCfg<HALF>::RB};
+}
+template <int HALF> constexpr FastEntry wide_entry()
+{
+    if constexpr (dev_on(HALF)) return FastEntry{launch_wide<HALF>, WideCfg<HALF>::NT, WideCfg<HALF>::SMEM, WideCfg<HALF>::RB};
+    else return FastEntry{nullptr, WideCfg<HALF>::NT, WideCfg<HALF>::SMEM, WideCfg<HALF>::RB};
+}
+template <int HALF> constexpr FastEntry ring_entry()
+{
+    if constexpr (dev_on(HALF)) return FastEntry{launch_ring<HALF>, RingCfg<HALF>::NT, RingCfg<HALF>::SMEM, 4};
+    else return FastEntry{nullptr, RingCfg<HALF>::NT, RingCfg<HALF>::SMEM, 4};
+}
+template <int HALF> constexpr FastEntry vh_entry()
+{
+    if constexpr (dev_on(HALF)) return FastEntry{launch_vh<HALF>, VhCfg<HALF>::NT, VhCfg<HALF>::SMEM, VhCfg<HALF>::CROWS};
+    else return FastEntry{nullptr, VhCfg<HALF>::NT, VhCfg<HALF>::SMEM, VhCfg<HALF>::CROWS};
 }
 // index [half][slot], slot 0/1/2 = 9/17/33 groups per chunk; h >= 5 has no 33-group instance (shared memory)
 const int kFastNgc[3] = {9, 17, 33};       // h >= 5 uses 18 in slot 1 (3 groups per phase-B thread, 384 threads: no register spills)
@@ -210,21 +277,32 @@ const FastEntry kFast[8][3] = {
     {fast_entry<7, 9>(), fast_entry<7, 18>(), FastEntry{nullptr, 0, 0, 0}}};
 
 // slot 3 = warp-specialised kernel (sad_ws.cuh): h <= 4, 33-group chunks, 32-column strips
-const FastEntry kWs[5] = {
-    FastEntry{launch_ws<0>, WsCfg<0>::NT, WsCfg<0>::SMEM, WsCfg<0>::RB}, FastEntry{launch_ws<1>, WsCfg<1>::NT, WsCfg<1>::SMEM, WsCfg<1>::RB},
-    FastEntry{launch_ws<2>, WsCfg<2>::NT, WsCfg<2>::SMEM, WsCfg<2>::RB}, FastEntry{launch_ws<3>, WsCfg<3>::NT, WsCfg<3>::SMEM, WsCfg<3>::RB},
-    FastEntry{launch_ws<4>, WsCfg<4>::NT, WsCfg<4>::SMEM, WsCfg<4>::RB}};
+const FastEntry kWs[5] = {ws_entry<0>(), ws_entry<1>(), ws_entry<2>(), ws_entry<3>(), ws_entry<4>()};
 
 // slot 4 = large-window kernel (sad_wide.cuh): h = 8..15, chunks of 8 groups
-#define WIDE_ENTRY(H) FastEntry{launch_wide<H>, WideCfg<H>::NT, WideCfg<H>::SMEM, WideCfg<H>::RB}
+#define WIDE_ENTRY(H) wide_entry<H>()
 const FastEntry kWide[8] = {WIDE_ENTRY(8), WIDE_ENTRY(9), WIDE_ENTRY(10), WIDE_ENTRY(11), WIDE_ENTRY(12), WIDE_ENTRY(13), WIDE_ENTRY(14), WIDE_ENTRY(15)};
+
+// slot 5 = vertical-first warp-specialised kernel (sad_vh.cuh): h = 5..15, 33-group chunks
+#define VH_ENTRY(H) vh_entry<H>()
+const FastEntry kVh[11] = {VH_ENTRY(5), VH_ENTRY(6), VH_ENTRY(7), VH_ENTRY(8), VH_ENTRY(9), VH_ENTRY(10), VH_ENTRY(11), VH_ENTRY(12),
+                           VH_ENTRY(13), VH_ENTRY(14), VH_ENTRY(15)};
+const int kVhTw[11] = {VhCfg<5>::TW, VhCfg<6>::TW, VhCfg<7>::TW, VhCfg<8>::TW, VhCfg<9>::TW, VhCfg<10>::TW, VhCfg<11>::TW, VhCfg<12>::TW,
+                       VhCfg<13>::TW, VhCfg<14>::TW, VhCfg<15>::TW};
+bool vh_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
+// slot 6 = shared-memory-ring warp-specialised kernel (sad_ring.cuh): h = 5..7, 33-group chunks, 32-column strips
+const FastEntry kRing[3] = {ring_entry<5>(), ring_entry<6>(), ring_entry<7>()};
+bool ring_supported(int B) { return B / 2 >= 5 && B / 2 <= 7; }
+bool ring_auto(int B, int D) { return ring_supported(B) && (D + 4) / 4 > 18; }   // faster than the register-ring fast path from 19 groups on (profiles/)
+
+bool vh_auto(int B, int D) { (void)B; (void)D; return false; }      // planner default: decided by measurement (profiles/)
 
 bool fast_supported(int B) { return B / 2 <= 7; }
 bool wide_supported(int B) { return B / 2 >= 8 && B / 2 <= 15; }
 bool ws_supported(int B, int D) { return B / 2 <= 4 && (D + 4) / 4 > 17; }
 
 int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, const sadgpu_tuning* t, int sm_count,
-                   FastPlan* p, int* slot_out, bool want_ws = false)
+                   FastPlan* p, int* slot_out, bool want_ws = false, bool want_vh = false, bool want_ring = false)
 {
     int rc = validate(w, h, B, D, y0, y1);
     if (rc) return rc;
@@ -241,11 +319,16 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
         slot = t->groups_per_chunk <= 9 ? 0 : t->groups_per_chunk <= 17 ? 1 : slot;
     }
     const bool ws = !wide && want_ws && ws_supported(B, D);
+    const bool vh = want_vh && vh_supported(B);
     if (ws) slot = 3;
     if (wide) slot = 4;
-    const FastEntry& fe = wide ? kWide[half - 8] : ws ? kWs[half] : kFast[half][slot];
-    const int tw = ws ? 32 : 64;
-    p->half = half; p->ngc = wide ? 8 : ws ? 33 : (slot == 1 && half >= 5) ? 18 : kFastNgc[slot]; p->rb = fe.rb;
+    const bool ring = want_ring && ring_supported(B);
+    if (vh) slot = 5;
+    if (ring) slot = 6;
+    const FastEntry& fe = ring ? kRing[half - 5] : vh ? kVh[half - 5] : wide ? kWide[half - 8] : ws ? kWs[half] : kFast[half][slot];
+    const int tw = ring ? 32 : vh ? kVhTw[half - 5] : ws ? 32 : 64;
+    p->tw = tw;
+    p->half = half; p->ngc = (vh || ring) ? 33 : wide ? 8 : ws ? 33 : (slot == 1 && half >= 5) ? 18 : kFastNgc[slot]; p->rb = fe.rb;
     a.NC = ceil_div(a.NG, p->ngc);
     p->nthreads = fe.nt; p->smem = fe.smem;
     const int rows = std::max(1, y1 - y0);
@@ -335,6 +418,8 @@ struct sadgpu_ctx {
     std::vector<std::pair<uint8_t*, size_t>> pool;
     bool attr_done[kMaxDevices][16];
     bool fast_attr_done[kMaxDevices][8][5];
+    bool vh_attr_done[kMaxDevices][11];
+    bool ring_attr_done[kMaxDevices][3];
     std::vector<size_t> dev_gkey_bytes;
     std::vector<uint32_t*> dev_gkey;       // per device scratch for sadgpu_compute_device
     std::mutex dev_mu;
@@ -377,7 +462,9 @@ int ensure_gkey(sadgpu_ctx* c, int dev_index, size_t bytes, uint32_t** out)
 int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, uint32_t* slot_gkey, cudaStream_t s)
 {
     const int variant = t ? t->kernel_variant : 0;
-    if (variant < 0 || variant > 4) return SADGPU_EINVAL;
+    if (variant < 0 || variant > 6) return SADGPU_EINVAL;
+    if (variant == 5 && !vh_supported(j.B)) return SADGPU_EINVAL;
+    if (variant == 6 && !ring_supported(j.B)) return SADGPU_EINVAL;
     if (variant == 2 && !fast_supported(j.B)) return SADGPU_EINVAL;
     if (variant == 3 && !ws_supported(j.B, j.D)) return SADGPU_EINVAL;
     if (variant == 4 && !wide_supported(j.B)) return SADGPU_EINVAL;
@@ -386,7 +473,8 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
     int launches = 0;
     if (use_fast) {
         FastPlan p; int slot = 0;
-        int rc = make_fast_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, j.n_frames, t, c->sm_count[dev_index], &p, &slot, want_ws);
+        int rc = make_fast_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, j.n_frames, t, c->sm_count[dev_index], &p, &slot, want_ws,
+                                variant == 5 || (variant == 0 && vh_auto(j.B, j.D)), variant == 6 || (variant == 0 && ring_auto(j.B, j.D)));
         if (rc) return rc;
         if (j.y1 == j.y0) return SADGPU_OK;
         FastArgs& a = p.a;
@@ -414,9 +502,11 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
             a.gkey = gk;
             sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 8192), 256, 0, s>>>(gk, n, 0xFFFFFFFFu);
         }
-        cudaError_t e = slot == 4 ? kWide[p.half - 8].fn(p, s, &c->fast_attr_done[dev_index][p.half - 8][4])
-                      : slot == 3 ? kWs[p.half].fn(p, s, &c->fast_attr_done[dev_index][p.half][3])
-                                  : kFast[p.half][slot].fn(p, s, &c->fast_attr_done[dev_index][p.half][slot]);
+        const FastEntry& fe = slot == 6 ? kRing[p.half - 5] : slot == 5 ? kVh[p.half - 5] : slot == 4 ? kWide[p.half - 8] : slot == 3 ? kWs[p.half] : kFast[p.half][slot];
+        bool* done = slot == 6 ? &c->ring_attr_done[dev_index][p.half - 5] : slot == 5 ? &c->vh_attr_done[dev_index][p.half - 5]
+                   : slot == 4 ? &c->fast_attr_done[dev_index][p.half - 8][4] : &c->fast_attr_done[dev_index][p.half][slot];
+        if (!fe.fn) return SADGPU_EINVAL;                              // developer build without this instance
+        cudaError_t e = fe.fn(p, s, done);
         if (e != cudaSuccess) return (int)e;
         if (a.NC > 1) {
             dim3 g(ceil_div(j.w, 256), j.y1 - j.y0, j.n_frames);
@@ -439,6 +529,7 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
                 const size_t n = (size_t)j.w * j.h;
                 sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, s>>>(gk, n, 0xFFFFFFFFu);
             }
+            if (!kLaunchGeneric[p.half]) return SADGPU_EINVAL;         // developer build without this instance
             cudaError_t e = kLaunchGeneric[p.half](p, s, &c->attr_done[dev_index][p.half]);
             if (e != cudaSuccess) return (int)e;
             if (p.a.NC > 1) {
@@ -581,6 +672,8 @@ int sadgpu_create(const int* devices, int n_devices, int max_w, int max_h, int n
     if (!c) return SADGPU_ENOMEM;
     memset(c->attr_done, 0, sizeof(c->attr_done));
     memset(c->fast_attr_done, 0, sizeof(c->fast_attr_done));
+    memset(c->vh_attr_done, 0, sizeof(c->vh_attr_done));
+    memset(c->ring_attr_done, 0, sizeof(c->ring_attr_done));
     c->max_w = max_w; c->max_h = max_h;
     for (int i = 0; i < n_devices; ++i) {
         const int d = devices ? devices[i] : i;
@@ -799,18 +892,21 @@ int sadgpu_last_launch_count(sadgpu_ctx* c) { return c ? c->last_launches.load()
 int sadgpu_plan_describe(int w, int h, int B, int D, int y0, int y1, const sadgpu_tuning* t, char* buf, size_t buflen)
 {
     const int variant = t ? t->kernel_variant : 0;
-    if (variant > 4 || (variant == 2 && !fast_supported(B)) || (variant == 4 && !wide_supported(B))) return SADGPU_EINVAL;
+    if (variant > 6 || (variant == 2 && !fast_supported(B)) || (variant == 4 && !wide_supported(B)) || (variant == 5 && !vh_supported(B)) ||
+        (variant == 6 && !ring_supported(B)))
+        return SADGPU_EINVAL;
     if (variant >= 2 || (variant == 0 && (fast_supported(B) || wide_supported(B)))) {
         FastPlan p; int slot = 0;
         const int nf = t && t->reserved[0] > 0 ? t->reserved[0] : 1;       // reserved[0]: frames per launch (describe only)
-        int rc = make_fast_plan(w, h, B, D, y0, y1, nf, t, 148, &p, &slot, variant == 3 || variant == 0);
+        int rc = make_fast_plan(w, h, B, D, y0, y1, nf, t, 148, &p, &slot, variant == 3 || variant == 0,
+                                variant == 5 || (variant == 0 && vh_auto(B, D)), variant == 6 || (variant == 0 && ring_auto(B, D)));
         if (rc) return rc;
         if (variant == 3 && slot != 3) return SADGPU_EINVAL;
         if (buf && buflen)
             snprintf(buf, buflen,
                      "{\"variant\":\"%s\",\"half\":%d,\"NG\":%d,\"NC\":%d,\"NGc\":%d,\"TW\":%d,\"RB\":%d,\"BH\":%d,"
                      "\"grid\":[%u,%u,%u],\"threads\":%d,\"smem\":%zu,\"launches\":%d,\"frames_per_launch\":%d}",
-                     slot == 4 ? "wide" : slot == 3 ? "warp-specialised" : "fast", p.half, p.a.NG, p.a.NC, p.ngc, slot == 3 ? 32 : 64, p.rb, p.a.BH,
+                     slot == 6 ? "ring" : slot == 5 ? "vertical-first" : slot == 4 ? "wide" : slot == 3 ? "warp-specialised" : "fast", p.half, p.a.NG, p.a.NC, p.ngc, p.tw, p.rb, p.a.BH,
                      p.grid.x, p.grid.y, p.grid.z, p.nthreads, p.smem, p.launches, nf);
         return SADGPU_OK;
     }

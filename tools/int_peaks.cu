@@ -23,15 +23,15 @@ constexpr int CHAINS = 8;
 enum Op { OP_IADD3, OP_VABSDIFF4, OP_VABSDIFF4_ACC, OP_PRMT, OP_LOP3, OP_IMAD, OP_VIADD16X2,
           OP_VIMNMX16X2, OP_VIMNMX, OP_VIMNMX3, OP_DP4A, OP_SHF, OP_MIX_IADD3_IMAD,
           OP_MIX_VABS_IMAD, OP_MIX_PRMT_IMAD, OP_MIX_VIMNMX_IMAD, OP_LDS128, OP_MIX_LDS128_IADD3,
-          OP_MIX_ALU3_IMAD1, OP_COUNT };
+          OP_MIX_ALU3_IMAD1, OP_REDUX_MIN, OP_SHFL_BFLY, OP_MIX_REDUX_8ALU, OP_MIX_SHFL_8ALU, OP_COUNT };
 
 static const char* op_name[OP_COUNT] = {
   "iadd3", "vabsdiff4", "vabsdiff4_acc", "prmt", "lop3", "imad", "viadd_16x2",
   "vimnmx_u16x2+lop3", "vimnmx_u32(min,max)", "vimnmx3_u32+viadd", "idp4a", "shf_funnel", "mix_iadd3+imad",
   "mix_vabsdiff4+imad", "mix_prmt+imad", "mix_vimnmx+imad", "lds128+lop3", "mix_lds128+4iadd3",
-  "mix_3alu+1imad" };
+  "mix_3alu+1imad", "redux_min_u32", "shfl_bfly", "mix_redux+8iadd3", "mix_shfl+8iadd3" };
 // instructions issued per chain per iteration
-static const int op_instr[OP_COUNT] = {1,1,1,1,1,1,1,2,2,2,1,1,2,2,2,2,2,5,4};
+static const int op_instr[OP_COUNT] = {1,1,1,1,1,1,1,2,2,2,1,1,2,2,2,2,2,5,4,1,1,9,9};
 
 template <int OP>
 __device__ __forceinline__ void step(uint32_t& a, uint32_t b, uint32_t c, const uint4* sm, uint32_t& addr) {
@@ -73,6 +73,30 @@ __device__ __forceinline__ void step(uint32_t& a, uint32_t b, uint32_t c, const 
     asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(v.z), "r"(v.w));
     asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(b), "r"(c));
     asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(c), "r"(b));
+  }
+  if constexpr (OP == OP_REDUX_MIN)    asm volatile("redux.sync.min.u32 %0, %0, 0xffffffff;" : "+r"(a));
+  if constexpr (OP == OP_SHFL_BFLY)    asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(a));
+  if constexpr (OP == OP_MIX_REDUX_8ALU) {
+    uint32_t r; asm volatile("redux.sync.min.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(a));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(r), "r"(c));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(b), "r"(c));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(c), "r"(b));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(b), "r"(c));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(c), "r"(b));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(b), "r"(c));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(c), "r"(b));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(b), "r"(c));
+  }
+  if constexpr (OP == OP_MIX_SHFL_8ALU) {
+    uint32_t r; asm volatile("shfl.sync.bfly.b32 %0, %1, 1, 0x1f, 0xffffffff;" : "=r"(r) : "r"(a));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(r), "r"(c));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(b), "r"(c));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(c), "r"(b));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(b), "r"(c));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(c), "r"(b));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(b), "r"(c));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(c), "r"(b));
+    asm volatile("add.u32 %0, %0, %1;\n\tadd.u32 %0, %0, %2;" : "+r"(a) : "r"(b), "r"(c));
   }
   if constexpr (OP == OP_MIX_ALU3_IMAD1) {
     asm volatile("vabsdiff4.u32.u32.u32 %0, %0, %1, %2;" : "+r"(a) : "r"(b), "r"(c));
