@@ -64,7 +64,8 @@ typedef struct sadgpu_tuning {
                                3 = warp-specialised fast path (block_size <= 9, max_disparity >= 68),
                                4 = large-window kernel (block_size 16..31),
                                5 = vertical-first mbarrier-pipelined kernel (block_size 10..31),
-                               6 = H-ring mbarrier-pipelined kernel (block_size 10..15; the default there for max_disparity >= 72) */
+                               6 = H-ring mbarrier-pipelined kernel (block_size 10..31; the default there whenever it needs fewer passes over the
+                                   disparity range than variants 2 / 4) */
     int reserved[4];        /* [0]: frames per launch (sadgpu_plan_describe only); [1]: developer flags (role idling, cycle counters);
                                [2] = 1: do not use TMA tile loads in the warp-specialised kernel */
 } sadgpu_tuning;

@@ -18,25 +18,35 @@
 #include <cuda_runtime.h>
 #include "sad_fast.cuh"
 
+#ifndef RING_WIDE_GT
+#define RING_WIDE_GT 2          // groups per consumer thread of the 17-group instances (3 -> 6 consumer warps, 2 -> 9)
+#endif
+
 namespace sadgpu {
 
 template <int HALF> struct RingCfg {
-    static_assert(HALF >= 1 && HALF <= 7, "ring kernel: 16-bit window sums, block_size <= 15");
+    static_assert(HALF >= 1 && HALF <= 15, "ring kernel: block_size <= 31");
     static constexpr int WIN = 2 * HALF + 1;
+    static constexpr bool WIDE = WIN * WIN * 255 >= 65536;          // h >= 8: window sums need 18 bits -> 32-bit consumer sums
     static constexpr int TW = 32, TWP = 33;
     static constexpr int NSTEP = TW + 2 * HALF;
     static constexpr int LW = (NSTEP + 3) & ~3;
-    static constexpr int NGC = 33, GT = 3, K = 11;
+    // h <= 7: chunks of 33 groups (walker lanes = 32 groups); h >= 8: the window needs up to 40 ring rows, so a chunk has 17
+    // groups (walker lanes = 16 groups x 2 column halves) and a ring row is half as large
+    static constexpr int NGC = WIDE ? 17 : 33, NGL = NGC - 1, GT = WIDE ? RING_WIDE_GT : 3, K = WIDE ? 18 / RING_WIDE_GT : 11;
+    static constexpr int NGS = GT * K;                              // group slots of an H row (>= NGC; the surplus slot is never valid)
     static constexpr int NWK = 4;                                   // walker warps = rows in flight (window + consumed burst + written burst <= NRH)
     // Ring sizes are multiples of the number of warps that take turns on them (8 walkers; 2 loaders x 4 rows), so that a
     // slot is always produced by the same warp: a parity wait is only sound for a waiter that has seen every phase.
-    static constexpr int NRH = 24;                                  // H ring rows: 2h+2 of the window + two bursts of NWK rows
+    static constexpr int OB = (WIN + NWK - 1) / NWK;                // a burst has left every window OB bursts later
+    static constexpr int NB = WIDE ? OB + 2 : 6;                    // bursts in the H ring: window + the burst being consumed + the one being written
+    static constexpr int NRH = NB * NWK;                            // H ring rows
     static constexpr int TR = 16;                                   // pixel-tile ring rows
     static constexpr int RT = 4, SEGW = 4;                          // tail walker: rows per step, columns per lane
     static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
     static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;
     static constexpr int RW = NGC - 1 + NWALKW;                     // words per aligned-R tile row
-    static constexpr int HROW = NGC * TWP;                          // uint2 per H row
+    static constexpr int HROW = NGS * TWP;                          // uint2 per H row
     static constexpr int NT = 768;
     // warp roles; SM sub-partition = warp % 4
     static constexpr int W_CONS = 8, W_TAIL = 19, W_FIN = 20, W_LD0 = 21, W_LD1 = 22, W_FIN2 = 23;
@@ -46,14 +56,13 @@ template <int HALF> struct RingCfg {
     static constexpr int OFF_PK = OFF_R + TR * RW * 4;              // [2][4][K][TW]
     static constexpr int OFF_LUT = OFF_PK + 2 * 4 * K * TW * 4;
     static constexpr int OFF_BAR = ((OFF_LUT + 1040 + 7) / 8) * 8;
-    static constexpr int WSPLIT = 2;                                // walker warps per row (column halves)
-    static constexpr int NB = NRH / NWK;                            // bursts in the H ring
-    static constexpr int OB = (WIN + NWK - 1) / NWK;                // a burst has left every window OB bursts later
+    static constexpr int WSPLIT = 2;                                // column halves of a row walk (two warps, or two half-warps when NGL = 16)
+    static constexpr int NWW = NWK * WSPLIT * NGL / 32;             // walker warps
     static constexpr int OB0 = (2 * HALF) / NWK;                    // first burst that holds an output row
     static constexpr int NBAR = 2 * NB + 2 * TR + 4;
     static constexpr int SMEM = OFF_BAR + NBAR * 8;
-    static_assert(GT * K == NGC && RT * (TW / SEGW) == 32 && W_CONS + K == W_TAIL, "roles");
-    static_assert(NWK == 4 && NWK * WSPLIT <= W_CONS && RT == NWK && NRH % NWK == 0 && TR % (2 * NWK) == 0, "every ring slot belongs to one producer warp");
+    static_assert(NGS >= NGC && RT * (TW / SEGW) == 32 && W_CONS + K <= W_TAIL && NWW <= W_CONS, "roles");
+    static_assert(NWK == 4 && RT == NWK && NRH % NWK == 0 && TR % (2 * NWK) == 0, "every ring slot belongs to one producer warp");
     static_assert(NB >= OB + 2, "ring: window bursts + the burst being consumed + the burst being written");
 };
 
@@ -159,12 +168,12 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
     for (int d = tid; d < 1040; d += C::NT) lut[d] = d <= a.D ? (uint8_t)((d * 255) / a.D) : 0;
     if (tid == 0) {
         for (int i = 0; i < NB; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(hfull + 8 * i), "n"(NWK * C::WSPLIT + 1));  // walkers + tail walker
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(hfull + 8 * i), "n"(C::NWW + 1));  // walkers + tail walker
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(hempty + 8 * i), "n"(K));
         }
         for (int i = 0; i < TR; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tfull + 8 * i));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tempty + 8 * i), "n"(C::WSPLIT + 1));   // walkers + tail walker
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tempty + 8 * i), "n"(C::NWW / NWK + 1));   // walkers + tail walker
         }
         for (int i = 0; i < 2; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(pkfull + 8 * i), "n"(K));
@@ -177,10 +186,11 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
     uint32_t* dbg = ((a.debug_skip & 4) && blockIdx.x == 7 && blockIdx.y == 0 && blockIdx.z == 0) ? a.gkey : nullptr;
     (void)dbg;
     RING_PROF_BEGIN;
-    if (warp < NWK * C::WSPLIT) {
-        // ---- walkers: warps w and w+NWK walk the two 16-column halves of row w of every burst for groups 0..31
-        //      (lanes = groups); the second half re-warms its window over 2h columns ----
-        const int wr = warp % NWK, wh = warp / NWK;
+    if (warp < C::NWW) {
+        // ---- walkers (lanes = groups): row w of every burst is walked in two 16-column halves — by warps w and w+NWK for
+        //      32-group chunks, by the two half-warps of warp w for 16-group chunks; the second half re-warms its window ----
+        const int wr = warp % NWK;
+        const int wh = C::NGL == 32 ? warp / NWK : lane >> 4, gl = lane & (C::NGL - 1);
         constexpr int HW = TW / C::WSPLIT;
         for (int bi = 0; bi < nbur; ++bi) {
             const int r = NWK * bi + wr, bs = bi % NB;
@@ -189,8 +199,8 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                 RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
                 if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
                 const uint32_t* Lr = Lrep + ts * LW + HW * wh;
-                const uint32_t* Rr = Ral + ts * RW + (NGC - 1 - lane) + (HW / 4) * wh;
-                uint2* Hout = Hs + (bs * NWK + wr) * HROW + lane * TWP + HW * wh;
+                const uint32_t* Rr = Ral + ts * RW + (NGC - 1 - gl) + (HW / 4) * wh;
+                uint2* Hout = Hs + (bs * NWK + wr) * HROW + gl * TWP + HW * wh;
                 if (nvalid >= C::NSTEP) ring_walk<HALF, HW, false>(Lr, Rr, Hout, nvalid - HW * wh, true);
                 else                    ring_walk<HALF, HW, true>(Lr, Rr, Hout, nvalid - HW * wh, true);
                 __syncwarp();
@@ -241,9 +251,11 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
         constexpr int GRP = 4;
         // interior strips (every tile column inside the image, 4-byte aligned rows): no per-lane tests in the load loop
         const bool interior = a.aligned && x0 - HALF >= 0 && x0 - HALF + LW <= a.W && xr0 >= 0 && xr0 + 4 * RW <= a.W;
-        const int li0 = min(lane, LW - 1), li1 = min(lane + 32, LW - 1);          // clamped: the surplus lanes reload a valid pixel
-        const int rj0 = min(lane, RW - 1), rj1 = min(lane + 32, RW - 1);
-        static_assert(NLQ == 2 && NRQ == 2, "two tile words per lane");
+        int lic[NLQ], rjc[NRQ];                                                   // clamped: the surplus lanes reload a valid element
+#pragma unroll
+        for (int q = 0; q < NLQ; ++q) lic[q] = x0 - HALF + min(lane + 32 * q, LW - 1);
+#pragma unroll
+        for (int q = 0; q < NRQ; ++q) rjc[q] = xr0 + 4 * min(lane + 32 * q, RW - 1);
         auto issue = [&](int t, uint32_t (&vl)[GRP][NLQ], uint32_t (&vr)[GRP][NRQ]) {      // global loads of the burst starting at row t
 #pragma unroll
             for (int u = 0; u < GRP; ++u) {
@@ -252,12 +264,10 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                 const uint8_t* pl = Lg + (size_t)(yin ? y : 0) * a.pitchL;
                 const uint8_t* pr = Rg + (size_t)(yin ? y : 0) * a.pitchR;
                 if (interior) {
-                    vl[u][0] = vl[u][1] = vr[u][0] = vr[u][1] = 0;
-                    if (yin) {
-                        vl[u][0] = pl[x0 - HALF + li0]; vl[u][1] = pl[x0 - HALF + li1];
-                        vr[u][0] = *reinterpret_cast<const uint32_t*>(pr + xr0 + 4 * rj0);
-                        vr[u][1] = *reinterpret_cast<const uint32_t*>(pr + xr0 + 4 * rj1);
-                    }
+#pragma unroll
+                    for (int q = 0; q < NLQ; ++q) vl[u][q] = yin ? (uint32_t)pl[lic[q]] : 0u;
+#pragma unroll
+                    for (int q = 0; q < NRQ; ++q) vr[u][q] = yin ? *reinterpret_cast<const uint32_t*>(pr + rjc[q]) : 0u;
                     continue;
                 }
 #pragma unroll
@@ -322,8 +332,9 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
 #pragma unroll
                 for (int kk = 0; kk < K; ++kk) best = min(best, pkb[(u * K + kk) * TW]);
                 if (x < HALF) best = 0;                      // sad.go:212-218: both windows clamp, d = 0 wins
-                if (a.NC == 1) Og[(size_t)y * a.pitchOut + x] = lut[best & 0xFFFFu];
-                else atomicMin(a.gkey + ((size_t)frame * a.H + y) * a.W + x, ((best >> 16) << 9) | (best & 511u));
+                if (a.NC == 1) Og[(size_t)y * a.pitchOut + x] = lut[best & (C::WIDE ? 511u : 0xFFFFu)];
+                else atomicMin(a.gkey + ((size_t)frame * a.H + y) * a.W + x,
+                               C::WIDE ? best : (((best >> 16) << 9) | (best & 511u)));
             }
             __syncwarp();
             if (lane == 0) ring_arrive(pkempty + 8 * (ob & 1));
@@ -334,30 +345,54 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
         const int kB = warp - C::W_CONS;
         const int xB = x0 + lane;
         const int dmax = min(a.D, xB - HALF);               // largest evaluated disparity of this column (sad.go:64-67, :212-218)
-        const uint32_t k16 = opaque(a.k65536);
-        uint32_t mE[GT], aE[GT], nE[GT], oE[GT], mO[GT], aO[GT], nO[GT], oO[GT];
-        uint32_t VE[GT], VO[GT];
+        // key constants: (sum << 16 | d) from 16x2-packed sums, or sum * 512 + d from 32-bit sums (h >= 8); a candidate that is
+        // never evaluated gets multiplier 0 / mask 0 and an all-ones addend
+        const uint32_t kmul = C::WIDE ? (opaque(a.k65536) >> 7) : opaque(a.k65536);
+        uint32_t mE[GT], aE[GT], nE[GT], oE[GT], mO[GT], aO[GT], nO[GT], oO[GT], m3E[GT], m3O[GT];
+        uint32_t VE[GT], VO[GT], V3[GT], V2[GT];          // narrow: VE/VO packed; wide: VE/VO raw low-lane sums, V3/V2 high-lane sums
 #pragma unroll
         for (int j = 0; j < GT; ++j) {
-            const int dG = 4 * (g0 + kB * GT + j);
-            const bool v3 = dG + 3 <= dmax, v1 = dG + 1 <= dmax, v2 = dG + 2 <= dmax, v0 = dG <= dmax;
-            mE[j] = v3 ? k16 : 0u; aE[j] = v3 ? (uint32_t)(dG + 3) : 0xFFFFFFFFu;
-            nE[j] = v1 ? 0xFFFF0000u : 0u; oE[j] = v1 ? (uint32_t)(dG + 1) : 0xFFFFFFFFu;
-            mO[j] = v2 ? k16 : 0u; aO[j] = v2 ? (uint32_t)(dG + 2) : 0xFFFFFFFFu;
-            nO[j] = v0 ? 0xFFFF0000u : 0u; oO[j] = v0 ? (uint32_t)dG : 0xFFFFFFFFu;
-            VE[j] = 0; VO[j] = 0;
+            const int gs = kB * GT + j;
+            const int dG = 4 * (g0 + gs);
+            const int dm = gs < NGC ? dmax : -1;             // surplus group slot: nothing valid
+            const bool v3 = dG + 3 <= dm, v1 = dG + 1 <= dm, v2 = dG + 2 <= dm, v0 = dG <= dm;
+            mE[j] = v3 ? kmul : 0u; aE[j] = v3 ? (uint32_t)(dG + 3) : 0xFFFFFFFFu;
+            mO[j] = v2 ? kmul : 0u; aO[j] = v2 ? (uint32_t)(dG + 2) : 0xFFFFFFFFu;
+            nE[j] = v1 ? (C::WIDE ? kmul : 0xFFFF0000u) : 0u; oE[j] = v1 ? (uint32_t)(dG + 1) : 0xFFFFFFFFu;
+            nO[j] = v0 ? (C::WIDE ? kmul : 0xFFFF0000u) : 0u; oO[j] = v0 ? (uint32_t)dG : 0xFFFFFFFFu;
+            m3E[j] = v3 ? 0u - (kmul << 16) : 0u;            // wide: -(2^25) removes the high lane from the raw low-lane sum
+            m3O[j] = v2 ? 0u - (kmul << 16) : 0u;
+            VE[j] = 0; VO[j] = 0; V3[j] = 0; V2[j] = 0;
         }
         const uint2* Hk = Hs + (kB * GT) * TWP + lane;
         auto keys = [&]() {
             uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
             for (int j = 0; j < GT; ++j) {
-                const uint32_t kEl = VE[j] * mE[j] + aE[j], kEh = (VE[j] & nE[j]) | oE[j];
-                const uint32_t kOl = VO[j] * mO[j] + aO[j], kOh = (VO[j] & nO[j]) | oO[j];
+                uint32_t kEl, kEh, kOl, kOh;
+                if (C::WIDE) {
+                    kEl = VE[j] * mE[j] + (V3[j] * m3E[j] + aE[j]); kEh = V3[j] * nE[j] + oE[j];
+                    kOl = VO[j] * mO[j] + (V2[j] * m3O[j] + aO[j]); kOh = V2[j] * nO[j] + oO[j];
+                } else {
+                    kEl = VE[j] * mE[j] + aE[j]; kEh = (VE[j] & nE[j]) | oE[j];
+                    kOl = VO[j] * mO[j] + aO[j]; kOh = (VO[j] & nO[j]) | oO[j];
+                }
                 best = min(best, min(kEl, kEh));
                 best = min(best, min(kOl, kOh));
             }
             return best;
+        };
+        // V += entering - leaving.  Wide: the packed difference is formed with a bias of 0x8000 in the low lane only, so
+        // that the low lane never borrows from the high lane; the arithmetic shift then yields the signed high-lane
+        // difference and the raw sum (bias removed in the same IADD3) carries low + 65536 * high.
+        auto update = [&](int j, uint2 n, uint2 o) {
+            if (C::WIDE) {
+                const uint32_t dE = n.x - o.x + 0x8000u, dO = n.y - o.y + 0x8000u;
+                VE[j] = VE[j] + dE - 0x8000u; V3[j] += (uint32_t)((int)dE >> 16);
+                VO[j] = VO[j] + dO - 0x8000u; V2[j] += (uint32_t)((int)dO >> 16);
+            } else {
+                VE[j] = VE[j] + n.x - o.x; VO[j] = VO[j] + n.y - o.y;
+            }
         };
         for (int bi = 0; bi < nbur; ++bi) {
             const int bs = bi % NB, ob = bi - OB0;
@@ -373,10 +408,7 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                     const uint2* Hn = Hk + (sn0 + u) * HROW;
                     const uint2* Ho = Hk + so * HROW;
 #pragma unroll
-                    for (int j = 0; j < GT; ++j) {
-                        const uint2 n = Hn[j * TWP], o = Ho[j * TWP];
-                        VE[j] = VE[j] + n.x - o.x; VO[j] = VO[j] + n.y - o.y;
-                    }
+                    for (int j = 0; j < GT; ++j) update(j, Hn[j * TWP], Ho[j * TWP]);
                     pkb[u * K * TW] = keys();
                 }
             } else {
@@ -384,14 +416,10 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                     const int r = NWK * bi + u;
                     if (r >= nin) break;
                     const uint2* Hn = Hk + (sn0 + u) * HROW;
+                    int so = sn0 + u - WIN; if (so < 0) so += NRH;
+                    const uint2* Ho = Hk + so * HROW;
 #pragma unroll
-                    for (int j = 0; j < GT; ++j) { const uint2 n = Hn[j * TWP]; VE[j] += n.x; VO[j] += n.y; }
-                    if (r >= WIN) {
-                        int so = sn0 + u - WIN; if (so < 0) so += NRH;
-                        const uint2* Ho = Hk + so * HROW;
-#pragma unroll
-                        for (int j = 0; j < GT; ++j) { const uint2 o = Ho[j * TWP]; VE[j] -= o.x; VO[j] -= o.y; }
-                    }
+                    for (int j = 0; j < GT; ++j) update(j, Hn[j * TWP], r >= WIN ? Ho[j * TWP] : make_uint2(0u, 0u));
                     if (r >= 2 * HALF) pkb[u * K * TW] = keys();
                 }
             }

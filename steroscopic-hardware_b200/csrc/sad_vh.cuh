@@ -23,6 +23,13 @@
 #include <cuda_runtime.h>
 #include "sad_fast.cuh"
 
+#ifndef VH_NLOAD
+#define VH_NLOAD 1        // loader warps (a second one measured slower: profiles/README.md)
+#endif
+#ifndef VH_DEFER
+#define VH_DEFER 1        // H warps finish a row one C-ring turn after walking it
+#endif
+
 namespace sadgpu {
 
 template <int HALF> struct VhCfg {
@@ -31,32 +38,33 @@ template <int HALF> struct VhCfg {
     static constexpr bool WIDE = WIN * WIN * 255 >= 65536;          // h >= 8: window sums need 18 bits
     static constexpr int NQ = 20, NCOL = 4 * NQ;                    // column quads / columns of C per strip
     static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;         // first column of the strip that the H walk uses
-    static constexpr int TW = (NCOL - 2 * HALF - OFF) & ~3;         // output columns per CTA
+    static constexpr int TW = (NCOL - 2 * HALF - OFF) & ~7;         // output columns per CTA (a multiple of the 8 tail segments)
     static constexpr int NSTEP = TW + 2 * HALF;                     // H walk length
     static constexpr int NCH = (TW + 31) / 32;
     static constexpr int NGC = 33;                                  // groups per chunk: 32 lanes + tail
     static constexpr int CP = 82;                                   // uint2 per (row, group): 164 words = 4 mod 32 -> 128-bit accesses conflict-free
     static constexpr int CROWS = 8;                                 // C ring rows = H warps
     static constexpr int PF = 8;                                    // rows the loader may run ahead
-    static constexpr int NR = WIN + 1 + PF;                         // pixel-tile ring rows
+    static constexpr int NR = ((WIN + 1 + PF + 7) / 8) * 8;         // pixel-tile ring rows (a multiple of 2 loaders x 4 rows: one loader per slot)
     static constexpr int RWS = 56;                                  // words per R tile row (NQ + NGC = 53 used)
     static constexpr int PKW = 73;                                  // words per best-key row
     static constexpr int NV = 10;                                   // V warps (2 quads each)
     static constexpr int NT = 768;
     // warp roles: warps 0..11 = V class (10 V, tail-V, loader), warps 12..23 = H class (8 H, tail-H, 3 idle); SM sub-partition = warp % 4
-    static constexpr int W_VT = 3, W_LD = 7, W_HT = 18;
+    static constexpr int W_VT = 3, W_LD = 7, W_HT = 18, W_LD2 = 20;
     static constexpr int C_BYTES = CROWS * NGC * CP * 8;
     static constexpr int OFF_L = C_BYTES;
     static constexpr int OFF_R = OFF_L + NR * NCOL * 4;
-    static constexpr int SG = (TW + 31) / 32;                       // outputs per lane of the tail-H warp (lanes = walk segments)
-    static constexpr int OFF_PK = OFF_R + NR * RWS * 4;             // [CROWS][PKW] best keys of groups 0..31
-    static constexpr int OFF_PKT = OFF_PK + CROWS * PKW * 4;        // [CROWS][PKW] keys of the tail group
-    static constexpr int OFF_LUT = ((OFF_PKT + CROWS * PKW * 4 + 15) / 16) * 16;
+    static constexpr int SG = TW / 8;                               // tail-H warp: lanes = 4 rows x 8 segments of SG outputs
+    static constexpr int PKR = 2 * CROWS;                           // best-key rows: a row is finished one C-ring turn after its walk
+    static constexpr int OFF_PK = OFF_R + NR * RWS * 4;             // [PKR][PKW] best keys of groups 0..31
+    static constexpr int OFF_PKT = OFF_PK + PKR * PKW * 4;          // [PKR][PKW] keys of the tail group
+    static constexpr int OFF_LUT = ((OFF_PKT + PKR * PKW * 4 + 15) / 16) * 16;
     static constexpr int OFF_BAR = OFF_LUT + 1040;
-    static constexpr int NBAR = 2 * NR + 4 * CROWS;
+    static constexpr int NBAR = 2 * NR + 2 * CROWS + 2 * PKR;
     static constexpr int SMEM = OFF_BAR + NBAR * 8;
     static constexpr int REGS_V = 56, REGS_H = 104;                 // setmaxnreg targets of the WIDE instances
-    static_assert(OFF + NSTEP <= NCOL && TW >= 32 && TW <= 2 * 32 + 8, "strip geometry");
+    static_assert(OFF + NSTEP <= NCOL && TW >= 32 && TW <= 2 * 32 + 8 && CROWS % 4 == 0, "strip geometry");
     static_assert(OFF_BAR % 8 == 0 && C_BYTES % 16 == 0, "alignment");
 };
 
@@ -183,13 +191,12 @@ __device__ __forceinline__ void vh_hwalk(const uint2* __restrict__ Crow, uint32_
 //      quickly); each lane warms its window up over 2h columns.  Crow = &C[slot][NGC-1][0]. ----
 template <int HALF, bool EDGE>
 __device__ __forceinline__ void vh_tailwalk(const uint2* __restrict__ Crow, uint32_t* __restrict__ pkrow, const VhKeys& K,
-                                            int t0, int lane)
+                                            int t0, int seg, bool act)
 {
     using T = VhCfg<HALF>;
-    constexpr int WIN = T::WIN, SG = T::SG, OFF = T::OFF, TW = T::TW;
-    const int j0 = lane * SG;
-    const bool act = j0 < TW;
-    const uint2* Cp = Crow + OFF + (act ? j0 : 0);
+    constexpr int WIN = T::WIN, SG = T::SG, OFF = T::OFF;
+    const int j0 = seg * SG;
+    const uint2* Cp = Crow + OFF + j0;
     uint32_t ce[SG + 2 * HALF], co[SG + 2 * HALF];
     uint32_t SE = 0, SO = 0, S3 = 0, S2 = 0;
 #pragma unroll
@@ -222,7 +229,7 @@ __device__ __forceinline__ void vh_tailwalk(const uint2* __restrict__ Crow, uint
         }
         uint32_t m = min(min(k3, k1), min(k2, k0));
         if (T::WIDE) m -= (uint32_t)(i + 1) << 24;
-        if (act && j0 + jj < TW) pkrow[j0 + jj] = m;
+        if (act) pkrow[j0 + jj] = m;
     }
 }
 
@@ -304,6 +311,92 @@ __device__ __forceinline__ void vh_vmarch(unsigned char* smem, int g, int cb, bo
     VH_PROF_END(dbg);
 }
 
+// ---- loaders: two warps take turns on groups of four rows; one row of replicated left pixels and aligned right words per
+//      tile slot; the global loads of a warp's next group are in flight while the current one waits for its slots ----
+template <int HALF>
+__device__ __forceinline__ void vh_loader(const FastArgs& a, unsigned char* smem, int li, int lane, int frame, int g0, int xq0,
+                                          int yb0, int nin, uint32_t* dbg)
+{
+    using T = VhCfg<HALF>;
+    constexpr int NR = T::NR, NCOL = T::NCOL, RWS = T::RWS, NGC = T::NGC;
+    uint32_t* Lrep = reinterpret_cast<uint32_t*>(smem + T::OFF_L);
+    uint32_t* Ral = reinterpret_cast<uint32_t*>(smem + T::OFF_R);
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(smem + T::OFF_BAR);
+    const uint32_t tfull = bar0, tempty = bar0 + 8 * NR;
+    const uint8_t* __restrict__ Lg = a.L + (long long)frame * a.frameL;
+    const uint8_t* __restrict__ Rg = a.R + (long long)frame * a.frameR;
+    const int xr0 = xq0 - 3 - 4 * (g0 + NGC - 1);   // image column of R tile word 0 (multiple of 4)
+    constexpr int NLQ = (NCOL + 31) / 32, NRQ = (RWS + 31) / 32;
+    int lx[NLQ], rx[NRQ], rmode[NRQ];
+#pragma unroll
+    for (int q = 0; q < NLQ; ++q) {
+        const int c = lane + 32 * q, x = xq0 + c;
+        lx[q] = (c < NCOL && (unsigned)x < (unsigned)a.W) ? x : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < NRQ; ++q) {
+        const int j = lane + 32 * q, x = xr0 + 4 * j;
+        const bool in = j < RWS && x + 3 >= 0 && x < a.W;
+        rx[q] = x;
+        rmode[q] = !in ? 0 : (a.aligned && x >= 0 && x + 3 < a.W) ? 1 : 2;
+    }
+    VH_PROF_BEGIN;
+    constexpr int GRP = 4;
+    auto issue = [&](int t, uint32_t (&vl)[GRP][NLQ], uint32_t (&vr)[GRP][NRQ]) {
+#pragma unroll
+        for (int u = 0; u < GRP; ++u) {
+            const int y = yb0 - HALF + t + u;
+            const bool yin = t + u < nin && (unsigned)y < (unsigned)a.H;
+            const uint8_t* pl = Lg + (size_t)(yin ? y : 0) * a.pitchL;
+            const uint8_t* pr = Rg + (size_t)(yin ? y : 0) * a.pitchR;
+#pragma unroll
+            for (int q = 0; q < NLQ; ++q) { vl[u][q] = 0; if (yin && lx[q] >= 0) vl[u][q] = pl[lx[q]]; }
+#pragma unroll
+            for (int q = 0; q < NRQ; ++q) {
+                uint32_t v = 0;
+                if (yin && rmode[q] == 1) v = *reinterpret_cast<const uint32_t*>(pr + rx[q]);
+                else if (yin && rmode[q] == 2) {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if ((unsigned)(rx[q] + b) < (unsigned)a.W) v |= (uint32_t)pr[rx[q] + b] << (8 * b);
+                }
+                vr[u][q] = v;
+            }
+        }
+    };
+    auto commit = [&](int t, uint32_t (&vl)[GRP][NLQ], uint32_t (&vr)[GRP][NRQ]) {
+#pragma unroll
+        for (int u = 0; u < GRP; ++u) {
+            const int r = t + u;
+            if (r >= nin) break;
+            const int slot = r % NR;
+            if (r >= NR) VH_WAIT(tempty + 8 * slot, (uint32_t)(r / NR - 1) & 1u, 2);
+            uint32_t* Ld = Lrep + slot * NCOL;
+            uint32_t* Rd = Ral + slot * RWS;
+#pragma unroll
+            for (int q = 0; q < NLQ; ++q) { const int c = lane + 32 * q; if (c < NCOL) Ld[c] = vl[u][q] * 0x01010101u; }
+#pragma unroll
+            for (int q = 0; q < NRQ; ++q) { const int j = lane + 32 * q; if (j < RWS) Rd[j] = vr[u][q]; }
+            __syncwarp();
+            if (lane == 0) vh_arrive(tfull + 8 * slot);
+        }
+    };
+    uint32_t vlA[GRP][NLQ], vrA[GRP][NRQ], vlB[GRP][NLQ], vrB[GRP][NRQ];
+    constexpr int ST = VH_NLOAD * GRP;               // rows between two groups of the same loader
+    int t = GRP * li;
+    if (t < nin) issue(t, vlA, vrA);
+    for (; t < nin; t += 2 * ST) {
+        const bool more = t + ST < nin;
+        if (more) issue(t + ST, vlB, vrB);
+        commit(t, vlA, vrA);
+        if (more) {
+            if (t + 2 * ST < nin) issue(t + 2 * ST, vlA, vrA);
+            commit(t + ST, vlB, vrB);
+        }
+    }
+    VH_PROF_END(dbg);
+}
+
 template <int HALF>
 __global__ void __launch_bounds__(VhCfg<HALF>::NT, 1) sad_vh_kernel(const __grid_constant__ FastArgs a)
 {
@@ -318,7 +411,7 @@ __global__ void __launch_bounds__(VhCfg<HALF>::NT, 1) sad_vh_kernel(const __grid
     uint8_t* lut = smem + T::OFF_LUT;
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(smem + T::OFF_BAR);
     const uint32_t tfull = bar0, tempty = bar0 + 8 * NR, cfull = bar0 + 16 * NR, cempty = cfull + 8 * CROWS;
-    const uint32_t tkfull = cempty + 8 * CROWS, tkempty = tkfull + 8 * CROWS;
+    const uint32_t tkfull = cempty + 8 * CROWS, tkempty = tkfull + 8 * T::PKR;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int frame = blockIdx.z / a.NC, chunk = blockIdx.z - frame * a.NC;
@@ -344,7 +437,7 @@ __global__ void __launch_bounds__(VhCfg<HALF>::NT, 1) sad_vh_kernel(const __grid
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(cfull + 8 * i), "n"(T::NV + 1));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"(cempty + 8 * i));
         }
-        for (int i = 0; i < CROWS; ++i) {
+        for (int i = 0; i < T::PKR; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tkfull + 8 * i));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tkempty + 8 * i));
         }
@@ -356,65 +449,7 @@ __global__ void __launch_bounds__(VhCfg<HALF>::NT, 1) sad_vh_kernel(const __grid
         // ============================ V class ============================
         if (T::WIDE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(T::REGS_V));
         if (warp == T::W_LD) {
-            // ---- loader: one row of replicated left pixels and aligned right words per tile slot, PF rows ahead ----
-            const uint8_t* __restrict__ Lg = a.L + (long long)frame * a.frameL;
-            const uint8_t* __restrict__ Rg = a.R + (long long)frame * a.frameR;
-            const int xr0 = xq0 - 3 - 4 * (g0 + NGC - 1);   // image column of R tile word 0 (multiple of 4)
-            constexpr int NLQ = (NCOL + 31) / 32, NRQ = (RWS + 31) / 32;
-            int lx[NLQ], rx[NRQ], rmode[NRQ];
-#pragma unroll
-            for (int q = 0; q < NLQ; ++q) {
-                const int c = lane + 32 * q, x = xq0 + c;
-                lx[q] = (c < NCOL && (unsigned)x < (unsigned)a.W) ? x : -1;
-            }
-#pragma unroll
-            for (int q = 0; q < NRQ; ++q) {
-                const int j = lane + 32 * q, x = xr0 + 4 * j;
-                const bool in = j < RWS && x + 3 >= 0 && x < a.W;
-                rx[q] = x;
-                rmode[q] = !in ? 0 : (a.aligned && x >= 0 && x + 3 < a.W) ? 1 : 2;
-            }
-            VH_PROF_BEGIN;
-            constexpr int GRP = 4;                           // rows whose global loads are in flight together
-            int slot = 0; uint32_t phe = 0;                  // parity of the tile_empty wait
-            for (int t = 0; t < nin; t += GRP) {
-                uint32_t vl[GRP][NLQ], vr[GRP][NRQ];
-#pragma unroll
-                for (int u = 0; u < GRP; ++u) {
-                    const int y = yb0 - HALF + t + u;
-                    const bool yin = t + u < nin && (unsigned)y < (unsigned)a.H;
-                    const uint8_t* pl = Lg + (size_t)(yin ? y : 0) * a.pitchL;
-                    const uint8_t* pr = Rg + (size_t)(yin ? y : 0) * a.pitchR;
-#pragma unroll
-                    for (int q = 0; q < NLQ; ++q) { vl[u][q] = 0; if (yin && lx[q] >= 0) vl[u][q] = pl[lx[q]]; }
-#pragma unroll
-                    for (int q = 0; q < NRQ; ++q) {
-                        uint32_t v = 0;
-                        if (yin && rmode[q] == 1) v = *reinterpret_cast<const uint32_t*>(pr + rx[q]);
-                        else if (yin && rmode[q] == 2) {
-#pragma unroll
-                            for (int b = 0; b < 4; ++b)
-                                if ((unsigned)(rx[q] + b) < (unsigned)a.W) v |= (uint32_t)pr[rx[q] + b] << (8 * b);
-                        }
-                        vr[u][q] = v;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < GRP; ++u) {
-                    if (t + u >= nin) break;
-                    if (t + u >= NR) VH_WAIT(tempty + 8 * slot, phe, 2);
-                    uint32_t* Ld = Lrep + slot * NCOL;
-                    uint32_t* Rd = Ral + slot * RWS;
-#pragma unroll
-                    for (int q = 0; q < NLQ; ++q) { const int c = lane + 32 * q; if (c < NCOL) Ld[c] = vl[u][q] * 0x01010101u; }
-#pragma unroll
-                    for (int q = 0; q < NRQ; ++q) { const int j = lane + 32 * q; if (j < RWS) Rd[j] = vr[u][q]; }
-                    __syncwarp();
-                    if (lane == 0) vh_arrive(tfull + 8 * slot);
-                    if (++slot == NR) { slot = 0; if (t + u >= NR) phe ^= 1u; }
-                }
-            }
-            VH_PROF_END(dbg);
+            vh_loader<HALF>(a, smem, 0, lane, frame, g0, xq0, yb0, nin, dbg);
         } else if (warp == T::W_VT) {
             const int q = lane < NQ ? lane : 0;
             if (nvalid >= NCOL) vh_vmarch<HALF, 4, false>(smem, NGC - 1, 4 * q, lane < NQ, lane, nin, nvalid, dbg);
@@ -439,17 +474,11 @@ __global__ void __launch_bounds__(VhCfg<HALF>::NT, 1) sad_vh_kernel(const __grid
             const int t0 = x0 - HALF - dG;
             const uint2* Crow = Cs + (hr * NGC + lane) * CP;
             VH_PROF_BEGIN;
-            const uint32_t* p0 = pk + hr * PKW;
-            const uint32_t* p1 = pkT + hr * PKW;
-            uint32_t ph = 0;
-            for (int k = hr; k < bhc; k += CROWS) {
-                VH_WAIT(cfull + 8 * hr, ph, 3);
-                if (edge_h) vh_hwalk<HALF, true, true>(Crow, pk + hr * PKW, K, t0, lane == 0);
-                else        vh_hwalk<HALF, false, true>(Crow, pk + hr * PKW, K, t0, lane == 0);
-                __syncwarp();
-                if (lane == 0) vh_arrive(cempty + 8 * hr);
-                // final min with the tail group, LUT, store
-                VH_WAIT(tkfull + 8 * hr, ph, 4);
+            auto finish = [&](int k) {                       // final min with the tail group, LUT, store of C row k
+                const int ps = k & (T::PKR - 1);
+                VH_WAIT(tkfull + 8 * ps, (uint32_t)(k / T::PKR) & 1u, 4);
+                const uint32_t* p0 = pk + ps * PKW;
+                const uint32_t* p1 = pkT + ps * PKW;
                 const int y = yb0 + k;
 #pragma unroll
                 for (int c = 0; c < T::NCH; ++c) {
@@ -463,26 +492,52 @@ __global__ void __launch_bounds__(VhCfg<HALF>::NT, 1) sad_vh_kernel(const __grid
                     }
                 }
                 __syncwarp();
-                if (lane == 0) vh_arrive(tkempty + 8 * hr);
+                if (lane == 0) vh_arrive(tkempty + 8 * ps);
+            };
+            uint32_t ph = 0;
+            int kprev = -1;
+            for (int k = hr; k < bhc; k += CROWS) {
+                VH_WAIT(cfull + 8 * hr, ph, 3);
+                uint32_t* pkrow = pk + (k & (T::PKR - 1)) * PKW;
+                if (edge_h) vh_hwalk<HALF, true, true>(Crow, pkrow, K, t0, lane == 0);
+                else        vh_hwalk<HALF, false, true>(Crow, pkrow, K, t0, lane == 0);
+                __syncwarp();
+                if (lane == 0) vh_arrive(cempty + 8 * hr);
+#if VH_DEFER
+                if (kprev >= 0) finish(kprev);               // one ring turn late: the tail keys of that row have long arrived
+                kprev = k;
+#else
+                finish(k);
+#endif
                 ph ^= 1u;
             }
+            if (kprev >= 0) finish(kprev);
             VH_PROF_END(dbg);
+        } else if (warp == T::W_LD2) {
+            if (VH_NLOAD == 2) vh_loader<HALF>(a, smem, 1, lane, frame, g0, xq0, yb0, nin, dbg);
         } else if (warp == T::W_HT) {
-            // ---- tail-H warp: group NGC-1, one C row at a time, lanes = segments of the walk ----
+            // ---- tail-H warp: group NGC-1 of four C rows at a time; lane = (row j, segment s of SG outputs).  Each lane
+            //      re-warms its window over 2h columns, so the segments are long and the rows few. ----
             const int dG = 4 * (g0 + NGC - 1);
             const VhKeys K = vh_make_keys<T::WIDE>(dG, a.D, opaque(a.k65536));
             const int t0 = x0 - HALF - dG;
             VH_PROF_BEGIN;
-            int cs = 0; uint32_t ph = 0;
-            for (int k = 0; k < bhc; ++k) {
-                VH_WAIT(cfull + 8 * cs, ph, 3);
-                if (k >= CROWS) VH_WAIT(tkempty + 8 * cs, ph ^ 1u, 5);
-                const uint2* Crow = Cs + (cs * NGC + NGC - 1) * CP;
-                if (edge_h) vh_tailwalk<HALF, true>(Crow, pkT + cs * PKW, K, t0, lane);
-                else        vh_tailwalk<HALF, false>(Crow, pkT + cs * PKW, K, t0, lane);
+            const int j = lane >> 3, sg = lane & 7;
+            for (int k = 0; k < bhc; k += 4) {
+                const int cs = (k & (CROWS - 1)) + j;
+                const uint32_t ph = (uint32_t)(k / CROWS) & 1u;
+                const bool act = k + j < bhc;
+                const int ps = (k + j) & (T::PKR - 1);
+                if (act) {
+                    VH_WAIT(cfull + 8 * cs, ph, 3);
+                    if (k + j >= T::PKR) VH_WAIT(tkempty + 8 * ps, (uint32_t)((k + j) / T::PKR - 1) & 1u, 5);
+                }
                 __syncwarp();
-                if (lane == 0) { vh_arrive(cempty + 8 * cs); vh_arrive(tkfull + 8 * cs); }
-                if (++cs == CROWS) { cs = 0; ph ^= 1u; }
+                const uint2* Crow = Cs + (cs * NGC + NGC - 1) * CP;
+                if (edge_h) vh_tailwalk<HALF, true>(Crow, pkT + ps * PKW, K, t0, sg, act);
+                else        vh_tailwalk<HALF, false>(Crow, pkT + ps * PKW, K, t0, sg, act);
+                __syncwarp();
+                if (act && sg == 0) { vh_arrive(cempty + 8 * cs); vh_arrive(tkfull + 8 * ps); }
             }
             VH_PROF_END(dbg);
         }

@@ -290,10 +290,19 @@ const FastEntry kVh[11] = {VH_ENTRY(5), VH_ENTRY(6), VH_ENTRY(7), VH_ENTRY(8), V
 const int kVhTw[11] = {VhCfg<5>::TW, VhCfg<6>::TW, VhCfg<7>::TW, VhCfg<8>::TW, VhCfg<9>::TW, VhCfg<10>::TW, VhCfg<11>::TW, VhCfg<12>::TW,
                        VhCfg<13>::TW, VhCfg<14>::TW, VhCfg<15>::TW};
 bool vh_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
-// slot 6 = shared-memory-ring warp-specialised kernel (sad_ring.cuh): h = 5..7, 33-group chunks, 32-column strips
-const FastEntry kRing[3] = {ring_entry<5>(), ring_entry<6>(), ring_entry<7>()};
-bool ring_supported(int B) { return B / 2 >= 5 && B / 2 <= 7; }
-bool ring_auto(int B, int D) { return ring_supported(B) && (D + 4) / 4 > 18; }   // faster than the register-ring fast path from 19 groups on (profiles/)
+// slot 6 = shared-memory-ring warp-specialised kernel (sad_ring.cuh): h = 5..15, 32-column strips, chunks of 33 groups (h <= 7) or 17
+const FastEntry kRing[11] = {ring_entry<5>(), ring_entry<6>(), ring_entry<7>(), ring_entry<8>(), ring_entry<9>(), ring_entry<10>(),
+                             ring_entry<11>(), ring_entry<12>(), ring_entry<13>(), ring_entry<14>(), ring_entry<15>()};
+bool ring_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
+// Planner default, from the measured variant sweep (profiles/r01_variant_sweep.json): a ring pass over 33 (17) groups costs about
+// 1.65x (1.7x) a pass of the phase-alternating kernels over 18 (8) groups, so the ring kernel wins whenever it needs fewer passes.
+bool ring_auto(int B, int D)
+{
+    if (!ring_supported(B)) return false;
+    const int ng = (D + 4) / 4;
+    if (B / 2 <= 7) return 165 * ((ng + 32) / 33) < 100 * ((ng + 17) / 18);
+    return 170 * ((ng + 16) / 17) < 100 * ((ng + 7) / 8);
+}   // faster than the register-ring fast path from 19 groups on (profiles/)
 
 bool vh_auto(int B, int D) { (void)B; (void)D; return false; }      // planner default: decided by measurement (profiles/)
 
@@ -328,7 +337,7 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
     const FastEntry& fe = ring ? kRing[half - 5] : vh ? kVh[half - 5] : wide ? kWide[half - 8] : ws ? kWs[half] : kFast[half][slot];
     const int tw = ring ? 32 : vh ? kVhTw[half - 5] : ws ? 32 : 64;
     p->tw = tw;
-    p->half = half; p->ngc = (vh || ring) ? 33 : wide ? 8 : ws ? 33 : (slot == 1 && half >= 5) ? 18 : kFastNgc[slot]; p->rb = fe.rb;
+    p->half = half; p->ngc = ring ? (half >= 8 ? 17 : 33) : vh ? 33 : wide ? 8 : ws ? 33 : (slot == 1 && half >= 5) ? 18 : kFastNgc[slot]; p->rb = fe.rb;
     a.NC = ceil_div(a.NG, p->ngc);
     p->nthreads = fe.nt; p->smem = fe.smem;
     const int rows = std::max(1, y1 - y0);
@@ -419,7 +428,7 @@ struct sadgpu_ctx {
     bool attr_done[kMaxDevices][16];
     bool fast_attr_done[kMaxDevices][8][5];
     bool vh_attr_done[kMaxDevices][11];
-    bool ring_attr_done[kMaxDevices][3];
+    bool ring_attr_done[kMaxDevices][11];
     std::vector<size_t> dev_gkey_bytes;
     std::vector<uint32_t*> dev_gkey;       // per device scratch for sadgpu_compute_device
     std::mutex dev_mu;

@@ -50,7 +50,7 @@ def test_plans_cover_the_parameter_surface(native):
                 elif p["variant"] == "wide":
                     assert 16 <= B <= 31
                 elif p["variant"] == "ring":
-                    assert 10 <= B <= 15 and D >= 72 and p["TW"] == 32
+                    assert 10 <= B <= 31 and p["TW"] == 32 and p["NGc"] == (33 if B <= 15 else 17)
                 else:
                     assert B <= 15
     assert despair.plan_describe(1920, 1080, 9, 128)["variant"] == "warp-specialised"
@@ -58,7 +58,9 @@ def test_plans_cover_the_parameter_surface(native):
     assert despair.plan_describe(1920, 1080, 15, 64)["variant"] == "fast"
     assert despair.plan_describe(1920, 1080, 15, 256, tuning=dict(kernel_variant=5))["variant"] == "vertical-first"
     assert despair.plan_describe(3840, 2160, 31, 256, tuning=dict(kernel_variant=5))["TW"] == 48
-    assert despair.plan_describe(1920, 1080, 31, 256)["variant"] == "wide"
+    assert despair.plan_describe(1920, 1080, 31, 256)["variant"] == "ring"
+    assert despair.plan_describe(1920, 1080, 31, 16)["variant"] == "wide"
+    assert despair.plan_describe(1920, 1080, 16, 64)["variant"] == "ring"        # the reference's start-up parameters (params.go:13-18)
     assert despair.plan_describe(1920, 1080, 31, 256, tuning=dict(kernel_variant=1))["variant"] == "generic"
     with pytest.raises(despair.SadGpuError):
         despair.plan_describe(1920, 1080, 31, 256, tuning=dict(kernel_variant=2))      # fast path needs block_size <= 15

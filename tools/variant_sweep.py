@@ -1,0 +1,30 @@
+"""Device-resident time of every kernel variant that supports a (B, D) point at 1080p -> gpurun_out/variant_sweep.json"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "steroscopic-hardware_b200"))
+import numpy as np, torch, despair
+W, H, F = 1920, 1080, 8
+ctx = despair.Context([0], W, H, 1)
+rng = np.random.default_rng(1)
+L = torch.from_numpy(rng.integers(0, 256, (F, H, W), dtype=np.uint8)).cuda(); R = torch.roll(L, -20, 2).contiguous(); O = torch.zeros_like(L)
+st = torch.cuda.current_stream().cuda_stream
+def t(B, D, v):
+    tun = dict(kernel_variant=v) if v else None
+    run = lambda: ctx.compute_device_batch(F, L.data_ptr(), W, W * H, R.data_ptr(), W, W * H, W, H, B, D, O.data_ptr(), W, W * H, cuda_stream=st, tuning=tun)
+    try:
+        for _ in range(2): run()
+    except despair.SadGpuError:
+        return None
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(3): run()
+    e1.record(); torch.cuda.synchronize()
+    return round(e0.elapsed_time(e1) * 1e3 / (3 * F), 1)
+out = []
+for B in (int(b) for b in os.environ.get("BS", "10,11,13,15,16,17,21,25,31").split(",")):
+    for D in (16, 32, 48, 64, 80, 96, 128, 192, 256):
+        row = {"B": B, "D": D, "auto": t(B, D, 0), "auto_variant": despair.plan_describe(W, H, B, D, frames=F)["variant"]}
+        for v, name in ((2, "fast"), (4, "wide"), (5, "vh"), (6, "ring")):
+            row[name] = t(B, D, v)
+        out.append(row); print(row, flush=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "variant_sweep.json"), "w"), indent=1)
