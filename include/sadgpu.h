@@ -107,6 +107,15 @@ int  sadgpu_submit_into(sadgpu_ctx *ctx, int stream,
                         int w, int h, int block_size, int max_disparity, int y0, int y1,
                         uint8_t *out, int out_stride, uint64_t *ticket);
 
+/* Video streams (BASELINE configs[4], examples/run.stream.go:33-67): n_frames frame pairs per call.  `pairs` is
+ * [n_frames][2][h][w] bytes (left plane, right plane, next pair ...; w a multiple of 4), `out` is [n_frames][h][w] and must lie
+ * in memory from sadgpu_host_alloc.  The batch travels as ONE H2D copy, ONE kernel launch that is many waves deep, and ONE
+ * D2H copy; sadgpu_wait(ctx, ticket, NULL, 0) synchronises.  sadgpu_reserve_batch sizes every stream's buffers for
+ * max_frames pairs (call it while no frame is in flight); a larger batch returns SADGPU_ERANGE. */
+int  sadgpu_reserve_batch(sadgpu_ctx *ctx, int max_frames);
+int  sadgpu_submit_batch_into(sadgpu_ctx *ctx, int stream, int n_frames, const uint8_t *pairs, int w, int h,
+                              int block_size, int max_disparity, uint8_t *out, uint64_t *ticket);
+
 /* One frame split into row bands with a block_size/2 halo over ALL devices of the context
  * (one band per device, streams 0..n_devices-1), host-side gather into out. */
 int  sadgpu_compute_sharded(sadgpu_ctx *ctx,

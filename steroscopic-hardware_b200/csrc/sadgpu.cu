@@ -413,6 +413,8 @@ struct Slot {
     uint64_t seq = 0;
     int w = 0, h = 0, y0 = 0, y1 = 0;                          // frame in flight
     bool out_direct = false;
+    int cap = 1;                                               // frame pairs the buffers hold (sadgpu_reserve_batch)
+    int nfr = 1;                                               // frames in flight
 };
 
 }  // namespace
@@ -468,7 +470,7 @@ int ensure_gkey(sadgpu_ctx* c, int dev_index, size_t bytes, uint32_t** out)
 
 // Enqueue one job (one frame, or a batch of frames) on stream s.  The device must be current.
 // Chooses the fast path (block_size <= 15) or the generic kernel; never a CPU path.
-int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, uint32_t* slot_gkey, cudaStream_t s)
+int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, uint32_t* slot_gkey, cudaStream_t s, int slot_gkey_frames = 1)
 {
     const int variant = t ? t->kernel_variant : 0;
     if (variant < 0 || variant > 6) return SADGPU_EINVAL;
@@ -507,7 +509,7 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
         if (a.NC > 1) {
             const size_t n = (size_t)j.n_frames * j.w * j.h;
             uint32_t* gk = slot_gkey;
-            if (!gk || j.n_frames > 1) { rc = ensure_gkey(c, dev_index, n * sizeof(uint32_t), &gk); if (rc) return rc; }
+            if (!gk || j.n_frames > slot_gkey_frames) { rc = ensure_gkey(c, dev_index, n * sizeof(uint32_t), &gk); if (rc) return rc; }
             a.gkey = gk;
             sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 8192), 256, 0, s>>>(gk, n, 0xFFFFFFFFu);
         }
@@ -646,6 +648,25 @@ int wait_locked(sadgpu_ctx* c, Slot* s, uint8_t* out, int out_stride)
     return SADGPU_OK;
 }
 
+// (Re)allocates the pinned and device buffers of a slot for `cap` frame pairs of max_w x max_h.
+cudaError_t alloc_slot_buffers(Slot* s, int max_w, int max_h, int cap)
+{
+    const size_t img = (size_t)round_up(max_w, 256) * (size_t)max_h;
+    cudaFreeHost(s->hL); cudaFreeHost(s->hOut); cudaFree(s->dL); cudaFree(s->dOut); cudaFree(s->gkey);
+    s->hL = s->hR = s->hOut = s->dL = s->dR = s->dOut = nullptr; s->gkey = nullptr;
+    cudaGetLastError();
+    // left and right live back to back (pinned and device) so that a whole frame pair is ONE DMA
+    cudaError_t e = cudaHostAlloc((void**)&s->hL, 2 * img * cap, cudaHostAllocPortable);
+    if (e == cudaSuccess) s->hR = s->hL + img;
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hOut, img * cap, cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->dL, 2 * img * cap);
+    if (e == cudaSuccess) s->dR = s->dL + img;
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->dOut, img * cap);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&s->gkey, (size_t)max_w * max_h * sizeof(uint32_t) * cap);
+    if (e == cudaSuccess) s->cap = cap;
+    return e;
+}
+
 void free_slot(Slot* s)
 {
     if (!s) return;
@@ -696,7 +717,6 @@ int sadgpu_create(const int* devices, int n_devices, int max_w, int max_h, int n
     c->dev_gkey.assign(n_devices, nullptr);
     c->dev_gkey_bytes.assign(n_devices, 0);
     const size_t pitch = (size_t)round_up(max_w, 256);
-    const size_t img = pitch * (size_t)max_h;
     for (int i = 0; i < n_streams; ++i) {
         Slot* s = new (std::nothrow) Slot();
         if (!s) { sadgpu_destroy(c); return SADGPU_ENOMEM; }
@@ -705,14 +725,7 @@ int sadgpu_create(const int* devices, int n_devices, int max_w, int max_h, int n
         e = cudaSetDevice(s->device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
-        // left and right live back to back (pinned and device) so that a whole frame pair is ONE DMA
-        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hL, 2 * img, cudaHostAllocPortable);
-        if (e == cudaSuccess) s->hR = s->hL + img;
-        if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hOut, img, cudaHostAllocPortable);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->dL, 2 * img);
-        if (e == cudaSuccess) s->dR = s->dL + img;
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->dOut, img);
-        if (e == cudaSuccess) e = cudaMalloc((void**)&s->gkey, (size_t)max_w * max_h * sizeof(uint32_t));
+        if (e == cudaSuccess) e = alloc_slot_buffers(s, max_w, max_h, 1);
         if (e != cudaSuccess) { sadgpu_destroy(c); return (int)e; }
     }
     *out = c;
@@ -777,6 +790,54 @@ int sadgpu_submit_into(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, cons
     if (s->busy) return SADGPU_EBUSY;
     rc = submit_locked(c, s, l, ls, r, rs, w, h, B, D, y0, y1, out, out_stride);
     if (rc) { cudaStreamSynchronize(s->st); s->busy = false; return rc; }
+    s->seq++;
+    *ticket = (s->seq << 16) | (uint64_t)stream;
+    return SADGPU_OK;
+}
+
+int sadgpu_reserve_batch(sadgpu_ctx* c, int max_frames)
+{
+    if (!c || max_frames < 1 || max_frames > 256) return SADGPU_EINVAL;
+    for (Slot* s : c->slots) {
+        std::lock_guard<std::mutex> g(s->mu);
+        if (s->busy) return SADGPU_EBUSY;
+        if (s->cap >= max_frames) continue;
+        cudaError_t e = cudaSetDevice(s->device);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+        if (e == cudaSuccess) e = alloc_slot_buffers(s, c->max_w, c->max_h, max_frames);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return SADGPU_OK;
+}
+
+int sadgpu_submit_batch_into(sadgpu_ctx* c, int stream, int n_frames, const uint8_t* pairs, int w, int h, int B, int D,
+                             uint8_t* out, uint64_t* ticket)
+{
+    if (!c || !pairs || !out || !ticket || n_frames < 1) return SADGPU_EINVAL;
+    if (stream < 0 || stream >= (int)c->slots.size()) return SADGPU_ERANGE;
+    if (w <= 0 || h <= 0 || w % 4) return SADGPU_EINVAL;           // contiguous frames: the pitch is w
+    if (w > c->max_w || h > c->max_h) return SADGPU_ERANGE;
+    int rc = validate(w, h, B, D, 0, h);
+    if (rc) return rc;
+    const size_t img = (size_t)w * h;
+    if (!in_pool(c, out, img * n_frames)) return SADGPU_EINVAL;    // the destination is retained until sadgpu_wait (cgo pointer rule)
+    Slot* s = c->slots[stream];
+    std::lock_guard<std::mutex> g(s->mu);
+    if (s->busy) return SADGPU_EBUSY;
+    if (n_frames > s->cap) return SADGPU_ERANGE;                   // sadgpu_reserve_batch first
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return (int)e;
+    const uint8_t* src = pairs;
+    if (!in_pool(c, pairs, 2 * img * n_frames)) { memcpy(s->hL, pairs, 2 * img * n_frames); src = s->hL; }   // pageable source: staged
+    e = cudaMemcpyAsync(s->dL, src, 2 * img * n_frames, cudaMemcpyHostToDevice, s->st);                     // ONE DMA for the batch
+    if (e != cudaSuccess) return (int)e;
+    Job j{s->dL, (size_t)w, (long long)(2 * img), s->dL + img, (size_t)w, (long long)(2 * img), s->dOut, (size_t)w, (long long)img,
+          n_frames, w, h, B, D, 0, h};
+    if ((rc = run_job(c, s->dev_index, j, nullptr, s->gkey, s->st, s->cap))) { cudaStreamSynchronize(s->st); return rc; }
+    e = cudaMemcpyAsync(out, s->dOut, img * n_frames, cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess) e = cudaEventRecord(s->done, s->st);
+    if (e != cudaSuccess) { cudaStreamSynchronize(s->st); return (int)e; }
+    s->busy = true; s->out_direct = true; s->w = w; s->h = h; s->y0 = 0; s->y1 = h; s->nfr = n_frames;
     s->seq++;
     *ticket = (s->seq << 16) | (uint64_t)stream;
     return SADGPU_OK;

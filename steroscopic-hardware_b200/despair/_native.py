@@ -28,6 +28,9 @@ EXPORTS = {
     "sadgpu_wait": (c_int, [c_void_p, ctypes.c_uint64, c_void_p, c_int]),
     "sadgpu_submit_into": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_int, c_int, c_void_p, c_int, ctypes.POINTER(ctypes.c_uint64)]),
+    "sadgpu_reserve_batch": (c_int, [c_void_p, c_int]),
+    "sadgpu_submit_batch_into": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                         ctypes.POINTER(ctypes.c_uint64)]),
     "sadgpu_compute_sharded": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                        c_void_p, c_int]),
     "sadgpu_compute_device": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int,

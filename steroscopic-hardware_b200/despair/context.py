@@ -80,6 +80,22 @@ class Context:
             N.check(self._L.sadgpu_wait(self._h, ticket, out.ctypes.data, out.strides[0]))
         return out
 
+    def reserve_batch(self, max_frames):
+        N.check(self._L.sadgpu_reserve_batch(self._h, max_frames))
+
+    def submit_batch(self, pairs, block_size, max_disparity, out, stream=0):
+        """pairs: uint8 [n][2][h][w] (contiguous; pinned pool memory avoids the staging copy); out: pool array [n][h][w]."""
+        p = np.asarray(pairs)
+        if p.dtype != np.uint8 or p.ndim != 4 or p.shape[1] != 2 or not p.flags.c_contiguous:
+            raise ValueError("pairs: expected a contiguous uint8 array [n][2][h][w]")
+        n, _, h, w = p.shape
+        if out.shape != (n, h, w) or not out.flags.c_contiguous:
+            raise ValueError("out: expected a contiguous uint8 array [n][h][w]")
+        t = ctypes.c_uint64()
+        N.check(self._L.sadgpu_submit_batch_into(self._h, stream, n, p.ctypes.data, w, h, block_size, max_disparity,
+                                                  out.ctypes.data, ctypes.byref(t)))
+        return t.value
+
     def compute_sharded(self, left, right, block_size, max_disparity, out=None):
         l = _u8_2d(left, "left"); r = _u8_2d(right, "right")
         h, w = l.shape

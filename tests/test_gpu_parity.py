@@ -275,6 +275,33 @@ def test_submit_into_pinned_destination(ctx, oracle):
     assert e.value.code == -1
 
 
+def test_submit_batch_video_stream(oracle):
+    """sadgpu_submit_batch_into: n frame pairs per call, one DMA each way, one launch; pinned and pageable sources;
+    chunked disparity range (key map per frame) and a wide window."""
+    import despair
+    c = despair.Context([0], 320, 120, 2)
+    try:
+        rng = np.random.default_rng(12)
+        with pytest.raises(despair.SadGpuError) as e:                   # capacity not reserved yet
+            c.submit_batch(np.zeros((3, 2, 120, 320), np.uint8), 9, 64, c.host_array((3, 120, 320)))
+        assert e.value.code == -2
+        c.reserve_batch(5)
+        for (B, D, n, pinned) in [(9, 128, 5, True), (15, 256, 4, False), (31, 40, 3, True), (5, 16, 1, False)]:
+            frames = [synth_pair(rng, 120, 320, k % 3) for k in range(n)]
+            pairs = c.host_array((n, 2, 120, 320)) if pinned else np.zeros((n, 2, 120, 320), np.uint8)
+            for k, (L, R) in enumerate(frames):
+                pairs[k, 0] = L; pairs[k, 1] = R
+            out = c.host_array((n, 120, 320)); out[:] = 3
+            c.wait(c.submit_batch(pairs, B, D, out, stream=n % 2))
+            for k, (L, R) in enumerate(frames):
+                assert np.array_equal(out[k], oracle.frame_box(L, R, B, D)), (B, D, k)
+        with pytest.raises(despair.SadGpuError) as e:                   # pageable destination refused
+            c.submit_batch(np.zeros((2, 2, 120, 320), np.uint8), 9, 64, np.zeros((2, 120, 320), np.uint8))
+        assert e.value.code == -1
+    finally:
+        c.close()
+
+
 def test_error_codes(ctx):
     import despair
     L = np.zeros((10, 10), np.uint8)
