@@ -126,7 +126,36 @@ def cpu_reference_run(frames_rows, threads, steps, warmup):
     return mpixd(frames, dt), dt / steps, out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else a library prints there (NCCL prints its
+    version banner on stdout at communicator creation) was diverted to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+def pin_to_gpu_numa(local_rank):
+    """Run this rank (and first-touch its pinned buffers) on the CPUs local to its GPU: the end-to-end leg is bound by
+    host memory and PCIe, and a rank on the far socket pays for every frame twice."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                      # fd 1 -> stderr for the rest of the run; emit() writes the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -156,7 +185,7 @@ def main():
                                  "sample": f"{rows} rows of one cfg3 frame per step, literal O(B^2 D) algorithm, "
                                            f"row bands of H/128 rows on {cores} pthreads"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -165,6 +194,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the SAD path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    affinity = pin_to_gpu_numa(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_streams = 4
@@ -347,9 +377,10 @@ def main():
                                            "frames_per_sec": e2e_steps * F * world / dt_single,
                                            "how": "sadgpu_submit_into/sadgpu_wait, one frame pair per call"}},
             "gpu_launches": args.steps * batches_per_step * launches_per_batch, "frames_per_launch": FB,
+            "host": {"cores": cores, "rank0_cpu_affinity": (f"{affinity[0]}-{affinity[-1]} ({len(affinity)} cpus, GPU-local)" if affinity else "unpinned")},
             "parity": parity, "plan": despair.plan_describe(W, H, B, D, frames=FB), "clocks": clocks,
             "roofline": roofline, "cpu_baseline": cpu_baseline}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
