@@ -17,6 +17,8 @@ HOST_LIB = os.path.join(HERE, "libdespair_host.so")
 HOST = os.path.join(HERE, "host")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
+# NOTE: do not add --split-compile: it cuts the build from 2.5 min to 45 s but the kernels it produces measured 10-25 %
+# slower on the B200 (cfg3 82.6 -> 94.0 us/frame, cfg4 2002 -> 2497 us).
 
 
 def _stale(target, sources):
@@ -27,7 +29,7 @@ def _stale(target, sources):
 
 
 def sources():
-    out = [os.path.join(ROOT, "include", "sadgpu.h")]
+    out = [os.path.join(ROOT, "include", "sadgpu.h"), os.path.abspath(__file__)]
     for f in sorted(os.listdir(CSRC)):
         if f.endswith((".cu", ".cuh", ".h", ".hpp", ".cpp")):
             out.append(os.path.join(CSRC, f))
@@ -37,7 +39,7 @@ def sources():
 def build_all(force=False, verbose=False):
     srcs = sources()
     if force or _stale(LIB, srcs):
-        cmd = ["nvcc"] + NVCC_FLAGS + ["-diag-suppress", "39", "-o", LIB, os.path.join(CSRC, "sadgpu.cu")]
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-diag-suppress", "39,177,1886", "-o", LIB, os.path.join(CSRC, "sadgpu.cu")]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
