@@ -420,6 +420,9 @@ __global__ void __launch_bounds__(VhCfg<HALF>::NT, 1) sad_vh_kernel(const __grid
     const int yb1 = min(a.y1, yb0 + a.BH);
     if (yb0 >= yb1) return;
     const int g0 = chunk * NGC;
+    // a chunk none of whose disparities is a candidate anywhere in this strip (d > X-h for every column, sad.go:64-67 + :212-218)
+    // has nothing to contribute: chunk 0 always runs and writes every pixel
+    if (g0 > 0 && min(x0 + TW, a.W) - 1 - HALF < 4 * g0) return;
     const int bhc = yb1 - yb0, nin = bhc + 2 * HALF;
     const int xq0 = x0 - HALF - T::OFF;                      // image column of C column 0 (= 3 mod 4)
     const int nvalid = a.W - xq0;                            // C columns >= nvalid lie right of the image

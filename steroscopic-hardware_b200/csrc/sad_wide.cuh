@@ -94,6 +94,9 @@ __global__ void __launch_bounds__(WideCfg<HALF>::NT, 1) sad_wide_kernel(const Fa
     const int yb1 = min(a.y1, yb0 + a.BH);
     const int g0 = chunk * NGC;
     if (yb0 >= yb1) return;
+    // a chunk none of whose disparities is a candidate anywhere in this strip (d > X-h for every column, sad.go:64-67 + :212-218)
+    // has nothing to contribute: chunk 0 always runs and writes every pixel
+    if (g0 > 0 && min(x0 + TW, a.W) - 1 - HALF < 4 * g0) return;
 
     for (int d = tid; d < 1040; d += NT) lut[d] = d <= a.D ? (uint8_t)((d * 255) / a.D) : 0;
 

@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid
     const int yb1 = min(a.y1, yb0 + a.BH);
     const int g0 = chunk * NGC;
     if (yb0 >= yb1) return;
+    // a chunk none of whose disparities is a candidate anywhere in this strip (d > X-h for every column, sad.go:64-67 + :212-218)
+    // has nothing to contribute: chunk 0 always runs and writes every pixel
+    if (g0 > 0 && min(x0 + TW, a.W) - 1 - HALF < 4 * g0) return;
     const int r0 = yb0 - HALF;
     const int nb = ((yb1 - yb0) + 2 * HALF + RB - 1) / RB;
     const int nvalid = a.W - (x0 - HALF);

@@ -275,6 +275,30 @@ def test_submit_into_pinned_destination(ctx, oracle):
     assert e.value.code == -1
 
 
+@pytest.mark.parametrize("B,D", [(9, 128), (15, 128), (13, 256), (16, 64), (31, 128)])
+def test_pipelined_kernels_are_deterministic_at_full_size(torch_mod, ctx, oracle, B, D):
+    """The warp-specialised kernels hand rows between warps through barriers; a protocol slip shows up as a rare wrong
+    tile, not as a crash.  Six launches of an 8-frame 1080p batch must agree bit for bit with each other, and a row range
+    of the first and the last frame with the oracle."""
+    rng = np.random.default_rng(80 + B)
+    F, H, W = 8, 1080, 1920
+    L = rng.integers(0, 256, (F, H, W), dtype=np.uint8); R = np.roll(L, -17, axis=2)
+    R[:, ::3] = rng.integers(0, 256, (F, (H + 2) // 3, W), dtype=np.uint8)
+    dL = torch_mod.from_numpy(L).cuda(); dR = torch_mod.from_numpy(R).cuda()
+    st = torch_mod.cuda.current_stream().cuda_stream
+    first = None
+    for rep in range(6):
+        dO = torch_mod.full((F, H, W), 77, dtype=torch_mod.uint8, device="cuda")
+        ctx.compute_device_batch(F, dL.data_ptr(), W, W * H, dR.data_ptr(), W, W * H, W, H, B, D, dO.data_ptr(), W, W * H, cuda_stream=st)
+        torch_mod.cuda.synchronize()
+        if first is None:
+            first = dO
+            for f in (0, F - 1):
+                assert np.array_equal(dO[f, 500:520].cpu().numpy(), oracle.frame_box(L[f], R[f], B, D, 500, 520)), (B, D, f)
+        else:
+            assert bool((dO == first).all()), (B, D, rep)
+
+
 def test_submit_batch_video_stream(oracle):
     """sadgpu_submit_batch_into: n frame pairs per call, one DMA each way, one launch; pinned and pageable sources;
     chunked disparity range (key map per frame) and a wide window."""
