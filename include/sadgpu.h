@@ -111,7 +111,8 @@ int  sadgpu_submit_into(sadgpu_ctx *ctx, int stream,
  * [n_frames][2][h][w] bytes (left plane, right plane, next pair ...; w a multiple of 4), `out` is [n_frames][h][w] and must lie
  * in memory from sadgpu_host_alloc.  The batch travels as ONE H2D copy, ONE kernel launch that is many waves deep, and ONE
  * D2H copy; sadgpu_wait(ctx, ticket, NULL, 0) synchronises.  sadgpu_reserve_batch sizes every stream's buffers for
- * max_frames pairs (call it while no frame is in flight); a larger batch returns SADGPU_ERANGE. */
+ * max_frames pairs up front (call it while no frame is in flight); a stream that meets a larger batch grows its own
+ * buffers on that call (n_frames <= 256). */
 int  sadgpu_reserve_batch(sadgpu_ctx *ctx, int max_frames);
 int  sadgpu_submit_batch_into(sadgpu_ctx *ctx, int stream, int n_frames, const uint8_t *pairs, int w, int h,
                               int block_size, int max_disparity, uint8_t *out, uint64_t *ticket);

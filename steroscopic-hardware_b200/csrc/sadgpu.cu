@@ -824,9 +824,14 @@ int sadgpu_submit_batch_into(sadgpu_ctx* c, int stream, int n_frames, const uint
     Slot* s = c->slots[stream];
     std::lock_guard<std::mutex> g(s->mu);
     if (s->busy) return SADGPU_EBUSY;
-    if (n_frames > s->cap) return SADGPU_ERANGE;                   // sadgpu_reserve_batch first
+    if (n_frames > 256) return SADGPU_ERANGE;
     cudaError_t e = cudaSetDevice(s->device);
     if (e != cudaSuccess) return (int)e;
+    if (n_frames > s->cap) {                                       // not pre-sized by sadgpu_reserve_batch: grow this stream's buffers now
+        e = cudaStreamSynchronize(s->st);
+        if (e == cudaSuccess) e = alloc_slot_buffers(s, c->max_w, c->max_h, n_frames);
+        if (e != cudaSuccess) return (int)e;
+    }
     const uint8_t* src = pairs;
     if (!in_pool(c, pairs, 2 * img * n_frames)) { memcpy(s->hL, pairs, 2 * img * n_frames); src = s->hL; }   // pageable source: staged
     e = cudaMemcpyAsync(s->dL, src, 2 * img * n_frames, cudaMemcpyHostToDevice, s->st);                     // ONE DMA for the batch

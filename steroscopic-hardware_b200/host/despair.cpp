@@ -167,7 +167,64 @@ Gray RunSad(const Gray& left, const Gray& right, int blockSize, int maxDisparity
 }  // namespace despair
 
 // ---- C hooks so that the Python test-suite can drive the C++ mirror (tests only) -------------------
+namespace despair {
+
+static PinnedFrames new_pinned(int n, int planes, int w, int h)
+{
+    PinnedFrames f;
+    f.base = static_cast<uint8_t*>(sadgpu_host_alloc(backend(), (size_t)n * planes * w * h));
+    if (!f.base) throw std::runtime_error("sadgpu_host_alloc failed");
+    f.n = n; f.planes = planes; f.w = w; f.h = h;
+    return f;
+}
+PinnedFrames NewPinnedPairs(int n, int w, int h) { return new_pinned(n, 2, w, h); }
+PinnedFrames NewPinnedMaps(int n, int w, int h) { return new_pinned(n, 1, w, h); }
+void FreePinned(PinnedFrames& f) { if (f.base) sadgpu_host_free(backend(), f.base); f = PinnedFrames{}; }
+
+void StreamSad(const PinnedFrames& pairs, PinnedFrames& maps, int batch, int depth)
+{
+    if (pairs.planes != 2 || maps.planes != 1 || pairs.n != maps.n || pairs.w != maps.w || pairs.h != maps.h || batch < 1)
+        throw std::runtime_error("StreamSad: mismatching frame sets");
+    sadgpu_ctx* g = backend();
+    const Parameters p = DefaultParams();                       // one snapshot per call (documented deviation: per chunk in Go)
+    depth = std::max(1, std::min(depth, g_streams));
+    int rc = SADGPU_OK;                                         // the `depth` streams used here grow their buffers on their first batch
+    std::vector<uint64_t> ticket(depth, 0);
+    std::vector<char> busy(depth, 0);
+    int call = 0, first_err = SADGPU_OK;
+    for (int i = 0; i < pairs.n; i += batch, ++call) {
+        const int s = call % depth, n = std::min(batch, pairs.n - i);
+        if (busy[s]) { rc = sadgpu_wait(g, ticket[s], nullptr, 0); busy[s] = 0; if (rc && !first_err) first_err = rc; }
+        rc = sadgpu_submit_batch_into(g, s, n, pairs.Left(i), pairs.w, pairs.h, p.BlockSize, p.MaxDisparity, maps.Map(i), &ticket[s]);
+        if (rc) { if (!first_err) first_err = rc; break; }
+        busy[s] = 1;
+    }
+    for (int s = 0; s < depth; ++s)
+        if (busy[s]) { rc = sadgpu_wait(g, ticket[s], nullptr, 0); if (rc && !first_err) first_err = rc; }
+    if (first_err) throw std::runtime_error(std::string("StreamSad: ") + sadgpu_strerror(first_err));
+}
+
+}  // namespace despair
+
 extern "C" {
+
+// Video path: n frame pairs through StreamSad (pinned pairs in, pinned maps out), results copied back for the test.
+int despair_host_stream(const uint8_t* left, const uint8_t* right, int n, int w, int h, int block_size, int max_disparity,
+                        int batch, uint8_t* out)
+{
+    try {
+        despair::SetDefaultParams(despair::Parameters{block_size, max_disparity});
+        despair::PinnedFrames pairs = despair::NewPinnedPairs(n, w, h), maps = despair::NewPinnedMaps(n, w, h);
+        for (int i = 0; i < n; ++i) {
+            memcpy(pairs.Left(i), left + (size_t)i * w * h, (size_t)w * h);
+            memcpy(pairs.Right(i), right + (size_t)i * w * h, (size_t)w * h);
+        }
+        despair::StreamSad(pairs, maps, batch);
+        memcpy(out, maps.base, (size_t)n * w * h);
+        despair::FreePinned(pairs); despair::FreePinned(maps);
+        return 0;
+    } catch (const std::exception&) { return -1; }
+}
 
 int despair_host_run_sad(const uint8_t* left, const uint8_t* right, int w, int h, int block_size, int max_disparity,
                          uint8_t* out)

@@ -105,6 +105,22 @@ Pipeline SetupConcurrentSAD(int numWorkers);
 Gray RunSad(const Gray& left, const Gray& right, int blockSize, int maxDisparity);
 Gray AssembleDisparityMap(Chan<OutputChunk>& outputChan, Rectangle dimensions, int chunks, bool faithful_drop = false);
 
+// Video path (examples/run.stream.go:33-67 without the per-frame channel traffic): frames live in the
+// backend's pinned pool, n pairs travel per GPU call (sadgpu_submit_batch_into), up to `depth` calls are in flight.
+// PinnedFrames owns [n][2][h][w] input pairs or [n][h][w] maps in pinned memory; Left(i)/Right(i)/Map(i) address one plane.
+struct PinnedFrames {
+    uint8_t* base = nullptr;
+    int n = 0, planes = 0, w = 0, h = 0;
+    uint8_t* Left(int i) const { return base + (size_t)i * planes * w * h; }
+    uint8_t* Right(int i) const { return Left(i) + (size_t)w * h; }
+    uint8_t* Map(int i) const { return base + (size_t)i * w * h; }
+};
+PinnedFrames NewPinnedPairs(int n, int w, int h);
+PinnedFrames NewPinnedMaps(int n, int w, int h);
+void FreePinned(PinnedFrames& f);
+// Disparity maps of `pairs` into `maps` with the current DefaultParams(), `batch` pairs per call.
+void StreamSad(const PinnedFrames& pairs, PinnedFrames& maps, int batch, int depth = 4);
+
 // Tile planner of RunSad (sad.go:128-153), exposed for tests.
 std::vector<Rectangle> RunSadChunks(Rectangle dims, int numCPU);
 

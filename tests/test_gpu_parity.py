@@ -306,10 +306,7 @@ def test_submit_batch_video_stream(oracle):
     c = despair.Context([0], 320, 120, 2)
     try:
         rng = np.random.default_rng(12)
-        with pytest.raises(despair.SadGpuError) as e:                   # capacity not reserved yet
-            c.submit_batch(np.zeros((3, 2, 120, 320), np.uint8), 9, 64, c.host_array((3, 120, 320)))
-        assert e.value.code == -2
-        c.reserve_batch(5)
+        c.reserve_batch(4)                                               # stream buffers for 4 pairs; the 5-pair batch grows its stream
         for (B, D, n, pinned) in [(9, 128, 5, True), (15, 256, 4, False), (31, 40, 3, True), (5, 16, 1, False)]:
             frames = [synth_pair(rng, 120, 320, k % 3) for k in range(n)]
             pairs = c.host_array((n, 2, 120, 320)) if pinned else np.zeros((n, 2, 120, 320), np.uint8)

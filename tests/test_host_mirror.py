@@ -20,6 +20,7 @@ def host():
     u8p = ctypes.c_void_p
     L.despair_host_run_sad.argtypes = [u8p, u8p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, u8p]
     L.despair_host_pipeline.argtypes = [u8p, u8p] + [ctypes.c_int] * 7 + [u8p, ctypes.POINTER(ctypes.c_int)]
+    L.despair_host_stream.argtypes = [u8p, u8p] + [ctypes.c_int] * 6 + [u8p]
     L.despair_host_run_sad_chunks.argtypes = [ctypes.c_int] * 3 + [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
     return L
 
@@ -48,6 +49,19 @@ def test_run_sad_on_gpu(host, oracle):
     out = np.zeros_like(L)
     assert host.despair_host_run_sad(L.ctypes.data, R.ctypes.data, 200, 120, 16, 64, out.ctypes.data) == 0
     assert np.array_equal(out, oracle.frame_box(L, R, 16, 64))
+
+
+@pytest.mark.gpu
+def test_stream_sad_video_path_on_gpu(host, oracle):
+    """StreamSad: pinned frame pairs in, pinned maps out, several pairs per GPU call (examples/run.stream.go:33-67)."""
+    rng = np.random.default_rng(6)
+    n, h, w = 11, 96, 160
+    base = rng.integers(0, 256, (n, h, w + 64), dtype=np.uint8)
+    L = np.ascontiguousarray(base[:, :, 64:]); R = np.ascontiguousarray(np.roll(base, -9, 2)[:, :, 64:])
+    out = np.zeros_like(L)
+    assert host.despair_host_stream(L.ctypes.data, R.ctypes.data, n, w, h, 11, 96, 4, out.ctypes.data) == 0
+    for i in range(n):
+        assert np.array_equal(out[i], oracle.frame_box(L[i], R[i], 11, 96)), i
 
 
 @pytest.mark.gpu
