@@ -14,8 +14,11 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 using namespace sadgpu;
@@ -400,6 +403,81 @@ bool make_tmap(CUtensorMap* m, const uint8_t* base, int w, int h, size_t pitch, 
 
 template <int HALF> void ws_box(int* lbox, int* rbox, int* rb) { *lbox = WsCfg<HALF>::LBOX; *rbox = WsCfg<HALF>::RWT * 4; *rb = WsCfg<HALF>::RB; }
 
+// Host-side staging copies (pageable caller memory <-> pinned buffers) are memory-bound single-thread memcpys of several
+// megabytes per frame; a few helper threads cut them to a fraction.  The pool is created with the context.
+class CopyPool {
+public:
+    explicit CopyPool(int helpers)
+    {
+        for (int i = 0; i < helpers; ++i) th_.emplace_back([this] { run(); });
+    }
+    ~CopyPool()
+    {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    // rows x width bytes, row pitches dp / sp; contiguous when dp == sp == width.  Small copies stay on the caller.
+    void copy(uint8_t* dst, size_t dp, const uint8_t* src, size_t sp, size_t width, size_t rows)
+    {
+        if (rows == 0 || width == 0) return;
+        const bool contig = dp == width && sp == width;
+        const size_t total = width * rows;
+        // waking a sleeping helper costs tens of microseconds on this class of host: only copies of 4 MB and more are split
+        // (measured: 1080p planes got slower when split three ways, 4K planes 20 % faster)
+        const int parts = total < (4u << 20) ? 1 : (int)std::min<size_t>(th_.size() + 1, total / (2u << 20));
+        if (parts <= 1) { one(dst, dp, src, sp, width, rows, contig); return; }
+        Latch latch{parts - 1};
+        for (int p = 1; p < parts; ++p) {
+            const size_t r0 = rows * p / parts, r1 = rows * (p + 1) / parts;
+            const size_t b0 = total * p / parts, b1 = total * (p + 1) / parts;
+            push([=, &latch] {
+                if (contig) memcpy(dst + b0, src + b0, b1 - b0);
+                else one(dst + r0 * dp, dp, src + r0 * sp, sp, width, r1 - r0, false);
+                latch.done();
+            });
+        }
+        if (contig) memcpy(dst, src, total / parts);
+        else one(dst, dp, src, sp, width, rows / parts, false);
+        latch.wait();
+    }
+private:
+    struct Latch {                      // lives on the caller's stack: the worker's last access is the decrement
+        std::atomic<int> n;
+        explicit Latch(int k) : n(k) {}
+        void done() { n.fetch_sub(1, std::memory_order_release); }
+        void wait() { while (n.load(std::memory_order_acquire) > 0) std::this_thread::yield(); }   // tens of microseconds
+    };
+    static void one(uint8_t* dst, size_t dp, const uint8_t* src, size_t sp, size_t width, size_t rows, bool contig)
+    {
+        if (contig) { memcpy(dst, src, width * rows); return; }
+        for (size_t y = 0; y < rows; ++y) memcpy(dst + y * dp, src + y * sp, width);
+    }
+    void push(std::function<void()> f)
+    {
+        { std::lock_guard<std::mutex> g(m_); q_.push_back(std::move(f)); }
+        cv_.notify_one();
+    }
+    void run()
+    {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_.wait(l, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                f = std::move(q_.front()); q_.erase(q_.begin());
+            }
+            f();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::vector<std::function<void()>> q_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
 struct Slot {
     int dev_index = 0, device = 0;
     cudaStream_t st = nullptr;
@@ -431,6 +509,7 @@ struct sadgpu_ctx {
     bool fast_attr_done[kMaxDevices][8][5];
     bool vh_attr_done[kMaxDevices][11];
     bool ring_attr_done[kMaxDevices][11];
+    CopyPool* copier = nullptr;
     std::vector<size_t> dev_gkey_bytes;
     std::vector<uint32_t*> dev_gkey;       // per device scratch for sadgpu_compute_device
     std::mutex dev_mu;
@@ -573,8 +652,8 @@ int upload(sadgpu_ctx* c, Slot* s, const uint8_t* src, int stride, uint8_t* pinn
     size_t from_pitch = (size_t)stride;
     if (!in_pool(c, from, (size_t)(n - 1) * stride + w)) {
         uint8_t* st = pinned + (size_t)ys * s->pitch;
-        if ((size_t)stride == s->pitch) memcpy(st, from, (size_t)(n - 1) * stride + w);
-        else for (int y = 0; y < n; ++y) memcpy(st + (size_t)y * s->pitch, from + (size_t)y * stride, (size_t)w);
+        if ((size_t)stride == s->pitch && s->pitch == (size_t)w) c->copier->copy(st, (size_t)w, from, (size_t)w, (size_t)w, (size_t)n);
+        else c->copier->copy(st, s->pitch, from, (size_t)stride, (size_t)w, (size_t)n);
         from = st; from_pitch = s->pitch;
     }
     cudaError_t e;
@@ -604,8 +683,12 @@ int submit_locked(sadgpu_ctx* c, Slot* s, const uint8_t* l, int ls, const uint8_
         cudaError_t e1 = cudaMemcpyAsync(s->dL, l, 2 * img, cudaMemcpyHostToDevice, s->st);
         if (e1 != cudaSuccess) return (int)e1;
     } else if (whole && !in_pool(c, l, img) && !in_pool(c, r, img)) {   // pageable pair: stage both, one DMA
-        memcpy(s->hL, l, img); memcpy(s->hR, r, img);
-        cudaError_t e1 = cudaMemcpyAsync(s->dL, s->hL, 2 * img, cudaMemcpyHostToDevice, s->st);
+        // pageable pair: stage the left plane, start its DMA, stage the right plane meanwhile
+        c->copier->copy(s->hL, img, l, img, img, 1);
+        cudaError_t e1 = cudaMemcpyAsync(s->dL, s->hL, img, cudaMemcpyHostToDevice, s->st);
+        if (e1 != cudaSuccess) return (int)e1;
+        c->copier->copy(s->hR, img, r, img, img, 1);
+        e1 = cudaMemcpyAsync(s->dR, s->hR, img, cudaMemcpyHostToDevice, s->st);
         if (e1 != cudaSuccess) return (int)e1;
     } else {
         if ((rc = upload(c, s, l, ls, s->hL, s->dL, w, ys, ye))) return rc;
@@ -632,7 +715,6 @@ int submit_locked(sadgpu_ctx* c, Slot* s, const uint8_t* l, int ls, const uint8_
 
 int wait_locked(sadgpu_ctx* c, Slot* s, uint8_t* out, int out_stride)
 {
-    (void)c;
     cudaError_t e = cudaSetDevice(s->device);
     if (e == cudaSuccess) e = cudaEventSynchronize(s->done);
     s->busy = false;
@@ -640,10 +722,11 @@ int wait_locked(sadgpu_ctx* c, Slot* s, uint8_t* out, int out_stride)
     if (!s->out_direct) {
         if (!out || out_stride < s->w) return SADGPU_EINVAL;
         if ((size_t)out_stride == s->pitch && s->pitch == (size_t)s->w)          // one contiguous block
-            memcpy(out + (size_t)s->y0 * out_stride, s->hOut + (size_t)s->y0 * s->pitch, (size_t)(s->y1 - s->y0) * s->w);
+            c->copier->copy(out + (size_t)s->y0 * out_stride, (size_t)s->w, s->hOut + (size_t)s->y0 * s->pitch, (size_t)s->w,
+                            (size_t)s->w, (size_t)(s->y1 - s->y0));
         else
-            for (int y = s->y0; y < s->y1; ++y)
-                memcpy(out + (size_t)y * out_stride, s->hOut + (size_t)y * s->pitch, (size_t)s->w);
+            c->copier->copy(out + (size_t)s->y0 * out_stride, (size_t)out_stride, s->hOut + (size_t)s->y0 * s->pitch, s->pitch,
+                            (size_t)s->w, (size_t)(s->y1 - s->y0));
     }
     return SADGPU_OK;
 }
@@ -714,6 +797,8 @@ int sadgpu_create(const int* devices, int n_devices, int max_w, int max_h, int n
         c->devices.push_back(d);
         c->sm_count.push_back(prop.multiProcessorCount);
     }
+    c->copier = new (std::nothrow) CopyPool((int)std::min(3u, std::max(1u, std::thread::hardware_concurrency() / 4)));
+    if (!c->copier) { delete c; return SADGPU_ENOMEM; }
     c->dev_gkey.assign(n_devices, nullptr);
     c->dev_gkey_bytes.assign(n_devices, 0);
     const size_t pitch = (size_t)round_up(max_w, 256);
@@ -739,6 +824,7 @@ void sadgpu_destroy(sadgpu_ctx* c)
     for (size_t i = 0; i < c->dev_gkey.size(); ++i)
         if (c->dev_gkey[i]) { cudaSetDevice(c->devices[i]); cudaFree(c->dev_gkey[i]); }
     for (auto& r : c->pool) cudaFreeHost(r.first);
+    delete c->copier;
     delete c;
 }
 
@@ -833,7 +919,10 @@ int sadgpu_submit_batch_into(sadgpu_ctx* c, int stream, int n_frames, const uint
         if (e != cudaSuccess) return (int)e;
     }
     const uint8_t* src = pairs;
-    if (!in_pool(c, pairs, 2 * img * n_frames)) { memcpy(s->hL, pairs, 2 * img * n_frames); src = s->hL; }   // pageable source: staged
+    if (!in_pool(c, pairs, 2 * img * n_frames)) {                  // pageable source: staged
+        c->copier->copy(s->hL, 2 * img * n_frames, pairs, 2 * img * n_frames, 2 * img * n_frames, 1);
+        src = s->hL;
+    }
     e = cudaMemcpyAsync(s->dL, src, 2 * img * n_frames, cudaMemcpyHostToDevice, s->st);                     // ONE DMA for the batch
     if (e != cudaSuccess) return (int)e;
     Job j{s->dL, (size_t)w, (long long)(2 * img), s->dL + img, (size_t)w, (long long)(2 * img), s->dOut, (size_t)w, (long long)img,
