@@ -354,7 +354,9 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
             const int bh = ceil_div(rows, nb);
             const long ctas = (long)nstrips * nb * a.NC * n_frames;
             const long waves = (ctas + sm_count - 1) / sm_count;
-            const long cost = waves * (round_up(bh + 2 * half, fe.rb) + fe.rb / 2 + 2);
+            // rows a CTA spends on pipeline fill and drain, beyond its band and the window halo
+            const int fill = ws ? 2 * fe.rb : (ring || vh) ? 12 : fe.rb / 2 + 2;
+            const long cost = waves * (round_up(bh + 2 * half, fe.rb) + fill);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; nbands = nb; }
         }
         a.BH = ceil_div(rows, nbands);

@@ -93,6 +93,13 @@ def test_tilings_do_not_change_pixels(torch_mod, ctx, oracle):
         if B <= 9 and D >= 68 and i % 3 == 0:
             tun = dict(band_rows=int(rng.integers(1, 50)), kernel_variant=3)
         assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, tun), oracle.frame_box(L, R, B, D)), (W, H, B, D, tun)
+    # the barrier-pipelined kernels: bands shorter than a burst / the window, one-row bands, bands that end mid-burst
+    for i in range(40):
+        W = int(rng.integers(20, 260)); H = int(rng.integers(10, 120))
+        B = int(rng.integers(10, 32)); D = int(rng.choice([5, 16, 64, 128, 256]))
+        L, R = synth_pair(rng, H, W, i % 5)
+        tun = dict(band_rows=int(rng.integers(1, 50)), kernel_variant=5 + i % 2)
+        assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, tun), oracle.frame_box(L, R, B, D)), (W, H, B, D, tun)
 
 
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
