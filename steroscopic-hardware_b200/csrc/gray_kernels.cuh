@@ -19,39 +19,62 @@ __device__ __forceinline__ uint32_t go_luma16(uint32_t r, uint32_t g, uint32_t b
     return (19595u * r + 38470u * g + 7471u * b + (1u << 15)) >> 24;     // max 65536*65535+32768 < 2^32
 }
 
+// Opaque pixel (alpha 255, or no alpha channel): c16 = c8*257 exactly, so the three multiplications by 257 fold into the
+// luma weights.  The weights sum to 65536, hence the sum stays below 65536*257*255 + 2^15 < 2^32.
+__device__ __forceinline__ uint32_t go_luma_opaque(uint32_t r, uint32_t g, uint32_t b)
+{
+    return (19595u * 257u * r + 38470u * 257u * g + 7471u * 257u * b + (1u << 15)) >> 24;
+}
+
 template <int MODE, int CH>
 __device__ __forceinline__ uint32_t gray_of(const uint8_t* p)
 {
     const uint32_t r = p[0], g = p[1], b = p[2];
     if (MODE == GRAY_RGBX8_LOADPNG) return (19595u * r + 38470u * g + 7471u * b + (1u << 15)) >> 24;   // always 0
-    if (MODE == GRAY_RGB8_INTENDED) return go_luma16(r * 257u, g * 257u, b * 257u);
-    const uint32_t a = CH == 4 ? p[3] : 255u;
-    return go_luma16(r * 257u * a / 255u, g * 257u * a / 255u, b * 257u * a / 255u);
+    if (MODE == GRAY_RGB8_INTENDED || CH == 3) return go_luma_opaque(r, g, b);
+    const uint32_t a = p[3];
+    if (a == 255u) return go_luma_opaque(r, g, b);          // the common case: three divisions by 255 saved (the kernel is ALU-bound with them)
+    const uint32_t a257 = a * 257u;
+    return go_luma16(r * a257 / 255u, g * a257 / 255u, b * a257 / 255u);
 }
+
+constexpr int kGrayRows = 4;      // rows per thread: four independent 16-byte loads in flight (the kernel is latency-, then HBM-bound)
 
 template <int MODE, int CH>
 __global__ void gray_kernel(const uint8_t* __restrict__ src, size_t src_pitch, uint8_t* __restrict__ dst, size_t dst_pitch,
                             int w, int h, int vec_ok)
 {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y;
-    if (x4 >= w || y >= h) return;
-    const uint8_t* row = src + (size_t)y * src_pitch;
-    uint8_t* out = dst + (size_t)y * dst_pitch;
+    const int y0 = blockIdx.y * kGrayRows;
+    if (x4 >= w) return;
     if (x4 + 3 < w && vec_ok) {
-        uint8_t px[4 * CH];
-        if (CH == 4) *reinterpret_cast<uint4*>(px) = *reinterpret_cast<const uint4*>(row + (size_t)x4 * 4);
-        else {
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(row + (size_t)x4 * 3);
+        uint32_t px[kGrayRows][CH];                         // 4 pixels = CH 32-bit words
 #pragma unroll
-            for (int k = 0; k < 3; ++k) reinterpret_cast<uint32_t*>(px)[k] = q[k];
+        for (int k = 0; k < kGrayRows; ++k) {
+            const int y = min(y0 + k, h - 1);               // clamped: surplus rows reload the last one
+            const uint8_t* row = src + (size_t)y * src_pitch;
+            if (CH == 4) {
+                const uint4 v = *reinterpret_cast<const uint4*>(row + (size_t)x4 * 4);
+                px[k][0] = v.x; px[k][1] = v.y; px[k][2] = v.z; px[k][CH - 1] = v.w;
+            } else {
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(row + (size_t)x4 * 3);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) px[k][j] = q[j];
+            }
         }
-        uint32_t v = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v |= gray_of<MODE, CH>(px + k * CH) << (8 * k);
-        *reinterpret_cast<uint32_t*>(out + x4) = v;
+        for (int k = 0; k < kGrayRows; ++k) {
+            if (y0 + k >= h) break;
+            const uint8_t* p = reinterpret_cast<const uint8_t*>(px[k]);
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v |= gray_of<MODE, CH>(p + j * CH) << (8 * j);
+            *reinterpret_cast<uint32_t*>(dst + (size_t)(y0 + k) * dst_pitch + x4) = v;
+        }
     } else {
-        for (int k = 0; k < 4 && x4 + k < w; ++k) out[x4 + k] = (uint8_t)gray_of<MODE, CH>(row + (size_t)(x4 + k) * CH);
+        for (int k = 0; k < kGrayRows && y0 + k < h; ++k)
+            for (int j = 0; j < 4 && x4 + j < w; ++j)
+                dst[(size_t)(y0 + k) * dst_pitch + x4 + j] = (uint8_t)gray_of<MODE, CH>(src + (size_t)(y0 + k) * src_pitch + (size_t)(x4 + j) * CH);
     }
 }
 

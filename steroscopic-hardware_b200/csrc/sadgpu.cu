@@ -1015,7 +1015,7 @@ int sadgpu_gray_device(sadgpu_ctx* c, int device, const uint8_t* dSrc, size_t sr
     if (e != cudaSuccess) return (int)e;
     cudaStream_t s = (cudaStream_t)cuda_stream;
     const int vec_ok = ((uintptr_t)dSrc % 16 == 0 && src_pitch % 16 == 0 && (uintptr_t)dGray % 4 == 0 && gray_pitch % 4 == 0) ? 1 : 0;
-    dim3 block(128), grid(ceil_div(ceil_div(w, 4), 128), h);
+    dim3 block(128), grid(ceil_div(ceil_div(w, 4), 128), ceil_div(h, kGrayRows));
     if (channels == 4 && mode == GRAY_NRGBA8)             gray_kernel<GRAY_NRGBA8, 4><<<grid, block, 0, s>>>(dSrc, src_pitch, dGray, gray_pitch, w, h, vec_ok);
     else if (channels == 3 && mode == GRAY_NRGBA8)        gray_kernel<GRAY_NRGBA8, 3><<<grid, block, 0, s>>>(dSrc, src_pitch, dGray, gray_pitch, w, h, vec_ok);
     else if (channels == 3 && mode == GRAY_RGB8_INTENDED) gray_kernel<GRAY_RGB8_INTENDED, 3><<<grid, block, 0, s>>>(dSrc, src_pitch, dGray, gray_pitch, w, h, vec_ok);

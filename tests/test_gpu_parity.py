@@ -376,6 +376,17 @@ def test_go_exact_gray_conversion_on_gpu(torch_mod, ctx):
         ctx.gray_device(d3.data_ptr(), w * 3, 3, 2, w, h, g.data_ptr(), w, cuda_stream=torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         assert not g.cpu().numpy().any()                                               # gray.go:35-37 as written
+    # every opaque colour (the folded-weights fast path) and every colour at three other alphas, 4096 x 4096 pixels each
+    idx = np.arange(1 << 24, dtype=np.uint32)
+    for alpha in (255, 254, 128, 3):
+        rgba = np.empty((1 << 24, 4), np.uint8)
+        rgba[:, 0] = idx & 255; rgba[:, 1] = (idx >> 8) & 255; rgba[:, 2] = idx >> 16; rgba[:, 3] = alpha
+        a = rgba.astype(np.uint64)
+        exp = _luma16((a[:, 0] * 257 * alpha) // 255, (a[:, 1] * 257 * alpha) // 255, (a[:, 2] * 257 * alpha) // 255).reshape(4096, 4096)
+        d = torch.from_numpy(rgba.reshape(4096, 4096 * 4)).cuda(); g = torch.zeros((4096, 4096), dtype=torch.uint8, device="cuda")
+        ctx.gray_device(d.data_ptr(), 4096 * 4, 4, 0, 4096, 4096, g.data_ptr(), 4096, cuda_stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(g.cpu().numpy(), exp), alpha
 
 
 def test_row_band_sharding_across_devices(torch_mod, oracle):
