@@ -88,6 +88,15 @@ int  sadgpu_compute(sadgpu_ctx *ctx, int stream,
                     int w, int h, int block_size, int max_disparity, int y0, int y1,
                     uint8_t *out, int out_stride);
 
+/* sadgpu_compute for a colour pair as Go decodes it: left / right are 8-bit NON-premultiplied RGBA planes,
+ * 4 bytes per pixel — the Pix of an *image.NRGBA, what image/png returns for an 8-bit RGBA PNG — and the 8-bit luma is taken
+ * on the device with the exact arithmetic of color.GrayModel.Convert (pkg/camera/output.go:143-147, :158-162; the same values
+ * as convertGenericToGray, pkg/despair/gray.go:43-58), so the per-pixel conversion loop of processDepthMap disappears.
+ * Whole frame, synchronous; strides in bytes (>= 4*w). */
+int  sadgpu_compute_nrgba(sadgpu_ctx *ctx, int stream,
+                          const uint8_t *left_rgba, int left_stride, const uint8_t *right_rgba, int right_stride,
+                          int w, int h, int block_size, int max_disparity, uint8_t *out, int out_stride);
+
 /* Asynchronous pair for per-camera pipelining.  submit copies the inputs (no caller pointer is
  * retained — cgo rule) and enqueues H2D + kernel + D2H on the stream; wait blocks until that
  * frame is done and copies rows [y0,y1) of the result to `out` (full-map addressing). */

@@ -493,6 +493,8 @@ struct Slot {
     uint64_t seq = 0;
     int w = 0, h = 0, y0 = 0, y1 = 0;                          // frame in flight
     bool out_direct = false;
+    uint8_t *hRGBA = nullptr, *dRGBA = nullptr;                // staging of the interleaved colour pair (sadgpu_compute_nrgba), lazily allocated
+    size_t rgba_bytes = 0;
     int cap = 1;                                               // frame pairs the buffers hold (sadgpu_reserve_batch)
     int nfr = 1;                                               // frames in flight
 };
@@ -667,6 +669,8 @@ int upload(sadgpu_ctx* c, Slot* s, const uint8_t* src, int stride, uint8_t* pinn
     return e == cudaSuccess ? SADGPU_OK : (int)e;
 }
 
+int finish_submit(sadgpu_ctx* c, Slot* s, int w, int h, int B, int D, int y0, int y1, uint8_t* direct_out, int direct_stride);
+
 int submit_locked(sadgpu_ctx* c, Slot* s, const uint8_t* l, int ls, const uint8_t* r, int rs,
                   int w, int h, int B, int D, int y0, int y1, uint8_t* direct_out, int direct_stride)
 {
@@ -696,6 +700,15 @@ int submit_locked(sadgpu_ctx* c, Slot* s, const uint8_t* l, int ls, const uint8_
         if ((rc = upload(c, s, l, ls, s->hL, s->dL, w, ys, ye))) return rc;
         if ((rc = upload(c, s, r, rs, s->hR, s->dR, w, ys, ye))) return rc;
     }
+    return finish_submit(c, s, w, h, B, D, y0, y1, direct_out, direct_stride);
+}
+
+// Second half of a submit: the frame pair is (being) uploaded to s->dL / s->dR on the slot's stream; enqueue the kernels
+// and the download of rows [y0,y1).
+int finish_submit(sadgpu_ctx* c, Slot* s, int w, int h, int B, int D, int y0, int y1, uint8_t* direct_out, int direct_stride)
+{
+    cudaError_t e = cudaSuccess;
+    int rc = SADGPU_OK;
     s->out_direct = direct_out != nullptr;
     if (y1 > y0) {
         Job j{s->dL, s->pitch, 0, s->dR, s->pitch, 0, s->dOut, s->pitch, 0, 1, w, h, B, D, y0, y1};
@@ -758,8 +771,8 @@ void free_slot(Slot* s)
     cudaSetDevice(s->device);
     if (s->st) { cudaStreamSynchronize(s->st); cudaStreamDestroy(s->st); }
     if (s->done) cudaEventDestroy(s->done);
-    cudaFreeHost(s->hL); cudaFreeHost(s->hOut);
-    cudaFree(s->dL); cudaFree(s->dOut); cudaFree(s->gkey);
+    cudaFreeHost(s->hL); cudaFreeHost(s->hOut); cudaFreeHost(s->hRGBA);
+    cudaFree(s->dL); cudaFree(s->dOut); cudaFree(s->gkey); cudaFree(s->dRGBA);
     delete s;
 }
 
@@ -843,6 +856,53 @@ int sadgpu_compute(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, const ui
     uint8_t* direct = nullptr;
     if (y1 > y0 && in_pool(c, out + (size_t)y0 * out_stride, (size_t)(y1 - y0 - 1) * out_stride + w)) direct = out;
     rc = submit_locked(c, s, l, ls, r, rs, w, h, B, D, y0, y1, direct, out_stride);
+    if (rc) { cudaStreamSynchronize(s->st); s->busy = false; return rc; }
+    return wait_locked(c, s, out, out_stride);
+}
+
+int sadgpu_compute_nrgba(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, const uint8_t* r, int rs,
+                         int w, int h, int B, int D, uint8_t* out, int out_stride)
+{
+    if (!c || !l || !r || !out) return SADGPU_EINVAL;
+    if (stream < 0 || stream >= (int)c->slots.size()) return SADGPU_ERANGE;
+    if (w <= 0 || h <= 0 || ls < 4 * w || rs < 4 * w || out_stride < w) return SADGPU_EINVAL;
+    if (w > c->max_w || h > c->max_h) return SADGPU_ERANGE;
+    int rc = validate(w, h, B, D, 0, h);
+    if (rc) return rc;
+    Slot* s = c->slots[stream];
+    std::lock_guard<std::mutex> g(s->mu);
+    if (s->busy) return SADGPU_EBUSY;
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return (int)e;
+    const size_t cpitch = (size_t)round_up(4 * w, 16), plane = cpitch * (size_t)h;     // 16-byte rows: vector loads in the luma kernel
+    if (s->rgba_bytes < 2 * plane) {
+        cudaStreamSynchronize(s->st);
+        cudaFreeHost(s->hRGBA); cudaFree(s->dRGBA); s->hRGBA = s->dRGBA = nullptr; s->rgba_bytes = 0;
+        e = cudaHostAlloc((void**)&s->hRGBA, 2 * plane, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&s->dRGBA, 2 * plane);
+        if (e != cudaSuccess) return (int)e;
+        s->rgba_bytes = 2 * plane;
+    }
+    s->pitch = (size_t)round_up(w, 4);
+    s->dR = s->dL + s->pitch * (size_t)h;
+    const uint8_t* src[2] = {l, r};
+    const int stride[2] = {ls, rs};
+    uint8_t* dgray[2] = {s->dL, s->dR};
+    for (int i = 0; i < 2; ++i) {                                  // stage (or take from the pinned pool), upload, luma on the device
+        const uint8_t* from = src[i];
+        size_t fpitch = (size_t)stride[i];
+        if (!in_pool(c, from, (size_t)(h - 1) * stride[i] + 4 * (size_t)w)) {
+            c->copier->copy(s->hRGBA + i * plane, cpitch, from, (size_t)stride[i], 4 * (size_t)w, (size_t)h);
+            from = s->hRGBA + i * plane; fpitch = cpitch;
+        }
+        e = cudaMemcpy2DAsync(s->dRGBA + i * plane, cpitch, from, fpitch, 4 * (size_t)w, (size_t)h, cudaMemcpyHostToDevice, s->st);
+        if (e != cudaSuccess) return (int)e;
+        dim3 block(128), grid(ceil_div(ceil_div(w, 4), 128), ceil_div(h, kGrayRows));
+        gray_kernel<GRAY_NRGBA8, 4><<<grid, block, 0, s->st>>>(s->dRGBA + i * plane, cpitch, dgray[i], s->pitch, w, h, 1);
+        if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    }
+    uint8_t* direct = in_pool(c, out, (size_t)(h - 1) * out_stride + w) ? out : nullptr;
+    rc = finish_submit(c, s, w, h, B, D, 0, h, direct, out_stride);
     if (rc) { cudaStreamSynchronize(s->st); s->busy = false; return rc; }
     return wait_locked(c, s, out, out_stride);
 }

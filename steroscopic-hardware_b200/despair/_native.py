@@ -23,6 +23,8 @@ EXPORTS = {
     "sadgpu_destroy": (None, [c_void_p]),
     "sadgpu_compute": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_void_p, c_int]),
+    "sadgpu_compute_nrgba": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_int]),
     "sadgpu_submit": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                               c_int, c_int, ctypes.POINTER(ctypes.c_uint64)]),
     "sadgpu_wait": (c_int, [c_void_p, ctypes.c_uint64, c_void_p, c_int]),

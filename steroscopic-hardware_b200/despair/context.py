@@ -57,6 +57,20 @@ class Context:
                                         w, h, block_size, max_disparity, y0, y1, out.ctypes.data, out.strides[0]))
         return out
 
+    def compute_nrgba(self, left_rgba, right_rgba, block_size, max_disparity, stream=0, out=None):
+        """left/right: uint8 [h][w][4] non-premultiplied RGBA (image.NRGBA.Pix); luma on the device, Go-exact."""
+        l = np.asarray(left_rgba); r = np.asarray(right_rgba)
+        if l.dtype != np.uint8 or l.ndim != 3 or l.shape[2] != 4 or l.shape != r.shape or r.dtype != np.uint8:
+            raise ValueError("expected two uint8 arrays [h][w][4] of the same shape")
+        if l.strides[2] != 1 or l.strides[1] != 4: l = np.ascontiguousarray(l)
+        if r.strides[2] != 1 or r.strides[1] != 4: r = np.ascontiguousarray(r)
+        h, w, _ = l.shape
+        if out is None:
+            out = np.zeros((h, w), np.uint8)
+        N.check(self._L.sadgpu_compute_nrgba(self._h, stream, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
+                                              w, h, block_size, max_disparity, out.ctypes.data, out.strides[0]))
+        return out
+
     def submit(self, left, right, block_size, max_disparity, y0=0, y1=None, stream=0, out=None):
         """Enqueue one frame.  With `out` (an array from host_array) the result is written there by the D2H copy
         itself (sadgpu_submit_into) and wait(ticket) needs no destination."""

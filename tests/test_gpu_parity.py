@@ -389,6 +389,28 @@ def test_go_exact_gray_conversion_on_gpu(torch_mod, ctx):
         assert np.array_equal(g.cpu().numpy(), exp), alpha
 
 
+def test_compute_nrgba_colour_pair(ctx, oracle, manifest):
+    """sadgpu_compute_nrgba: the RGBA crops cut from the reference testdata go in as image.NRGBA.Pix would,
+    the luma is taken on the device, the map equals the oracle's on the Go-exact luma; pinned and pageable, odd strides."""
+    from PIL import Image
+    from oracle.go_image import load_png
+    m = manifest["rgba_crop"]
+    pl = os.path.join(GOLDEN, f"L_{m['tag']}_rgba_crop.png"); pr = os.path.join(GOLDEN, f"R_{m['tag']}_rgba_crop.png")
+    L4 = np.array(Image.open(pl)); R4 = np.array(Image.open(pr))
+    assert L4.shape == (m["h"], m["w"], 4) and int((L4[..., 3] < 255).sum() + (R4[..., 3] < 255).sum()) == m["pixels_with_alpha_below_255"]
+    gl = load_png(pl, "intended"); gr = load_png(pr, "intended")
+    for (B, D) in ((9, 64), (16, 64), (15, 128)):
+        exp = oracle.frame_box(gl, gr, B, D)
+        assert np.array_equal(ctx.compute_nrgba(L4, R4, B, D), exp), (B, D)
+    assert sha(ctx.compute_nrgba(L4, R4, 9, 64)) == m["b9_d64_sha256"]
+    # row stride larger than 4*w (a sub-image of a wider NRGBA), odd width, pinned destination
+    wide = np.zeros((m["h"], m["w"] + 7, 4), np.uint8); wide[:, 3:3 + 301] = L4[:, :301]
+    wide_r = np.zeros_like(wide); wide_r[:, 3:3 + 301] = R4[:, :301]
+    out = ctx.host_array((m["h"], 301))
+    ctx.compute_nrgba(wide[:, 3:3 + 301], wide_r[:, 3:3 + 301], 9, 64, out=out)
+    assert np.array_equal(out, oracle.frame_box(np.ascontiguousarray(gl[:, :301]), np.ascontiguousarray(gr[:, :301]), 9, 64))
+
+
 def test_row_band_sharding_across_devices(torch_mod, oracle):
     """cfg4-style: one frame split into row bands with a block-size halo over every visible GPU of the box
     (sadgpu_compute_sharded), host-side gather; frames of a stream round-robin over devices (stream s -> device s % n)."""

@@ -160,3 +160,17 @@ def test_chunk_planners_and_assemble_bug(oracle):
     assert np.array_equal(bug, exp)
     assert np.array_equal(oracle.assemble_disparity_map(chunks, 40, 24, len(bands), faithful_bug=False), full)
     assert not oracle.assemble_disparity_map(chunks[:1], 40, 24, 1).any()   # chunks==1 -> all zero
+
+
+def test_rgba_crop_fixture_is_pinned(oracle):
+    """The colour fixture of sadgpu_compute_nrgba: Go-exact luma of the RGBA crops (alpha < 255 on 1 589 pixels) and the
+    oracle's map reproduce the SHA-256 values recorded when the fixture was cut from the reference testdata."""
+    import hashlib, json, os
+    from conftest import GOLDEN
+    from oracle.go_image import load_png
+    m = json.load(open(os.path.join(GOLDEN, "manifest.json")))["rgba_crop"]
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    L = load_png(os.path.join(GOLDEN, f"L_{m['tag']}_rgba_crop.png"), "intended")
+    R = load_png(os.path.join(GOLDEN, f"R_{m['tag']}_rgba_crop.png"), "intended")
+    assert L.shape == (m["h"], m["w"]) and sha(L) == m["left_gray_sha256"] and sha(R) == m["right_gray_sha256"]
+    assert sha(oracle.frame_box(L, R, 9, 64)) == m["b9_d64_sha256"]
