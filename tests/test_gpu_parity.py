@@ -219,22 +219,25 @@ def test_cfg4_4k_b31_d256_rows_and_properties(ctx, oracle):
     assert np.array_equal(got2[15:-15], got[55:-15])
 
 
-def test_submit_wait_pipelining_and_sharded(ctx, oracle):
+@pytest.mark.parametrize("B,D", [(9, 64), (9, 128), (15, 128), (16, 64)])
+def test_submit_wait_pipelining_and_sharded(ctx, oracle, B, D):
+    """Four streams in flight (kernels of different frames overlap on the device) for every planner default:
+    phase-alternating, warp-specialised + TMA, H-ring with 33- and 17-group chunks."""
     rng = np.random.default_rng(9)
     frames = [synth_pair(rng, 120, 320, 1) for _ in range(8)]
-    exp = [oracle.frame_box(L, R, 9, 64) for L, R in frames]
+    exp = [oracle.frame_box(L, R, B, D) for L, R in frames]
     outs = [np.zeros((120, 320), np.uint8) for _ in frames]
     tickets = {}
     for k, (L, R) in enumerate(frames):
         s = k % 4
         if s in tickets:
             kk, t = tickets.pop(s); ctx.wait(t, outs[kk])
-        tickets[s] = (k, ctx.submit(L, R, 9, 64, stream=s))
+        tickets[s] = (k, ctx.submit(L, R, B, D, stream=s))
     for s, (kk, t) in tickets.items():
         ctx.wait(t, outs[kk])
     for o, e in zip(outs, exp):
         assert np.array_equal(o, e)
-    assert np.array_equal(ctx.compute_sharded(frames[0][0], frames[0][1], 9, 64), exp[0])
+    assert np.array_equal(ctx.compute_sharded(frames[0][0], frames[0][1], B, D), exp[0])
 
 
 def test_pinned_pool_zero_copy_path(ctx, oracle):
