@@ -24,6 +24,11 @@
 
 namespace sadgpu {
 
+#ifndef RING_BURST8_MAX_HALF
+#define RING_BURST8_MAX_HALF 11   // largest h whose ring (window + two bursts of 8 rows of 17 groups) fits shared memory
+#endif
+constexpr bool SMEM_OK(int bytes) { return bytes + 1024 <= 232448; }
+
 template <int HALF> struct RingCfg {
     static_assert(HALF >= 1 && HALF <= 15, "ring kernel: block_size <= 31");
     static constexpr int WIN = 2 * HALF + 1;
@@ -35,14 +40,17 @@ template <int HALF> struct RingCfg {
     // groups (walker lanes = 16 groups x 2 column halves) and a ring row is half as large
     static constexpr int NGC = WIDE ? 17 : 33, NGL = NGC - 1, GT = WIDE ? RING_WIDE_GT : 3, K = WIDE ? 18 / RING_WIDE_GT : 11;
     static constexpr int NGS = GT * K;                              // group slots of an H row (>= NGC; the surplus slot is never valid)
-    static constexpr int NWK = 4;                                   // walker warps = rows in flight (window + consumed burst + written burst <= NRH)
+    // rows per burst.  17-group rows are small enough for bursts of 8 up to h = 11: the walkers then take whole 32-column rows
+    // (lanes = 16 groups x 2 rows) instead of re-warming 16-column halves
+    static constexpr int NWK = (WIDE && HALF <= RING_BURST8_MAX_HALF) ? 8 : 4;
+    static constexpr int WMODE = !WIDE ? 0 : NWK == 4 ? 1 : 2;       // 0: warp = (row, column half); 1: warp = row, half-warps = column halves; 2: warp = row pair, half-warps = rows
     // Ring sizes are multiples of the number of warps that take turns on them (8 walkers; 2 loaders x 4 rows), so that a
     // slot is always produced by the same warp: a parity wait is only sound for a waiter that has seen every phase.
     static constexpr int OB = (WIN + NWK - 1) / NWK;                // a burst has left every window OB bursts later
     static constexpr int NB = WIDE ? OB + 2 : 6;                    // bursts in the H ring: window + the burst being consumed + the one being written
     static constexpr int NRH = NB * NWK;                            // H ring rows
     static constexpr int TR = 16;                                   // pixel-tile ring rows
-    static constexpr int RT = 4, SEGW = 4;                          // tail walker: rows per step, columns per lane
+    static constexpr int RT = NWK, NSEG = 32 / RT, SEGW = TW / NSEG;  // tail walker: lane = (row of the burst, segment of SEGW columns)
     static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
     static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;
     static constexpr int RW = NGC - 1 + NWALKW;                     // words per aligned-R tile row
@@ -53,16 +61,18 @@ template <int HALF> struct RingCfg {
     static constexpr int H_BYTES = NRH * HROW * 8;
     static constexpr int OFF_L = ((H_BYTES + 15) / 16) * 16;
     static constexpr int OFF_R = OFF_L + TR * LW * 4;
-    static constexpr int OFF_PK = OFF_R + TR * RW * 4;              // [2][4][K][TW]
-    static constexpr int OFF_LUT = OFF_PK + 2 * 4 * K * TW * 4;
+    static constexpr int OFF_PK = OFF_R + TR * RW * 4;              // [2][NWK][K][TW]
+    static constexpr int OFF_LUT = OFF_PK + 2 * NWK * K * TW * 4;
     static constexpr int OFF_BAR = ((OFF_LUT + 1040 + 7) / 8) * 8;
-    static constexpr int WSPLIT = 2;                                // column halves of a row walk (two warps, or two half-warps when NGL = 16)
-    static constexpr int NWW = NWK * WSPLIT * NGL / 32;             // walker warps
+    static constexpr int WSPLIT = WMODE == 2 ? 1 : 2;               // column segments of a row walk
+    static constexpr int NWW = WMODE == 0 ? NWK * 2 : WMODE == 1 ? NWK : NWK / 2;    // walker warps
+    static constexpr int TEC = (WMODE == 0 ? 2 : 1) + 1;            // arrivals that free a pixel-tile row: its walker warps + the tail walker
     static constexpr int OB0 = (2 * HALF) / NWK;                    // first burst that holds an output row
     static constexpr int NBAR = 2 * NB + 2 * TR + 4;
     static constexpr int SMEM = OFF_BAR + NBAR * 8;
-    static_assert(NGS >= NGC && RT * (TW / SEGW) == 32 && W_CONS + K <= W_TAIL && NWW <= W_CONS, "roles");
-    static_assert(NWK == 4 && RT == NWK && NRH % NWK == 0 && TR % (2 * NWK) == 0, "every ring slot belongs to one producer warp");
+    static_assert(NGS >= NGC && RT * NSEG == 32 && SEGW % 4 == 0 && W_CONS + K <= W_TAIL && NWW <= W_CONS, "roles");
+    static_assert((NWK == 4 || NWK == 8) && NRH % NWK == 0 && TR % 8 == 0 && TR % NWK == 0, "every ring slot belongs to one producer warp");
+    static_assert(SMEM_OK(OFF_BAR), "shared memory");
     static_assert(NB >= OB + 2, "ring: window bursts + the burst being consumed + the burst being written");
 };
 
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
         }
         for (int i = 0; i < TR; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tfull + 8 * i));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tempty + 8 * i), "n"(C::NWW / NWK + 1));   // walkers + tail walker
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tempty + 8 * i), "n"(C::TEC));   // walkers + tail walker
         }
         for (int i = 0; i < 2; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(pkfull + 8 * i), "n"(K));
@@ -190,30 +200,35 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
     (void)dbg;
     RING_PROF_BEGIN;
     if (warp < C::NWW) {
-        // ---- walkers (lanes = groups): row w of every burst is walked in two 16-column halves — by warps w and w+NWK for
-        //      32-group chunks, by the two half-warps of warp w for 16-group chunks; the second half re-warms its window ----
-        const int wr = warp % NWK;
-        const int wh = C::NGL == 32 ? warp / NWK : lane >> 4, gl = lane & (C::NGL - 1);
+        // ---- walkers (lanes = groups).  33-group chunks: warps w and w+NWK walk the two 16-column halves of row w of every
+        //      burst.  17-group chunks: the two half-warps of warp w walk the halves of row w (bursts of 4), or whole rows
+        //      2w and 2w+1 (bursts of 8).  A half re-warms its window over 2h columns. ----
+        const int hw = lane >> 4;
+        const int wr = C::WMODE == 0 ? warp % NWK : C::WMODE == 1 ? warp : 2 * warp + hw;      // row of the burst
+        const int wh = C::WMODE == 0 ? warp / NWK : C::WMODE == 1 ? hw : 0;                    // column segment
+        const int gl = lane & (C::NGL - 1);
         constexpr int HW = TW / C::WSPLIT;
         for (int bi = 0; bi < nbur; ++bi) {
             const int r = NWK * bi + wr, bs = bi % NB;
-            if (r < nin) {
-                const int ts = r % TR;
-                RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
-                if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
+            const bool act = r < nin;                          // uniform per warp except in mode 2 (one row per half-warp)
+            const int ts = r % TR;
+            if (act) RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
+            if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
+            __syncwarp();
+            if (C::WMODE == 2 || act) {
                 const uint32_t* Lr = Lrep + ts * LW + HW * wh;
                 const uint32_t* Rr = Ral + ts * RW + (NGC - 1 - gl) + (HW / 4) * wh;
                 uint2* Hout = Hs + (bs * NWK + wr) * HROW + gl * TWP + HW * wh;
-                if (nvalid >= C::NSTEP) ring_walk<HALF, HW, false>(Lr, Rr, Hout, nvalid - HW * wh, true);
-                else                    ring_walk<HALF, HW, true>(Lr, Rr, Hout, nvalid - HW * wh, true);
-                __syncwarp();
-                if (lane == 0) ring_arrive(tempty + 8 * ts);
+                if (nvalid >= C::NSTEP) ring_walk<HALF, HW, false>(Lr, Rr, Hout, nvalid - HW * wh, act);
+                else                    ring_walk<HALF, HW, true>(Lr, Rr, Hout, nvalid - HW * wh, act);
             }
+            __syncwarp();
+            if (act && (lane == 0 || (C::WMODE == 2 && lane == 16))) ring_arrive(tempty + 8 * ts);
             if (lane == 0) ring_arrive(hfull + 8 * bs);
         }
     } else if (warp == C::W_TAIL) {
-        // ---- tail walker: group NGC-1 of the four rows of a burst; lane = (row j, segment s of SEGW columns) ----
-        const int j = lane >> 3, s = lane & 7;
+        // ---- tail walker: group NGC-1 of the rows of a burst; lane = (row j, segment s of SEGW columns) ----
+        const int j = lane / C::NSEG, s = lane % C::NSEG;
         for (int bi = 0; bi < nbur; ++bi) {
             const int r = NWK * bi + j, bs = bi % NB;
             const bool act = r < nin;
@@ -222,7 +237,7 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
             if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
             __syncwarp();
             const uint32_t* Lr = Lrep + ts * LW + C::SEGW * s;
-            const uint32_t* Rr = Ral + ts * RW + s;
+            const uint32_t* Rr = Ral + ts * RW + (C::SEGW / 4) * s;
             uint2* Hout = Hs + (bs * NWK + j) * HROW + (NGC - 1) * TWP + C::SEGW * s;
             if (nvalid >= C::NSTEP) ring_walk<HALF, C::SEGW, false>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
             else                    ring_walk<HALF, C::SEGW, true>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
@@ -320,14 +335,14 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
         }
     } else if (warp == C::W_FIN || warp == C::W_FIN2) {
         // ---- finishers: min over the K partial keys of a pixel, LUT, store; each warp takes two rows of every burst ----
-        const int fh = warp == C::W_FIN ? 0 : 2;
+        const int fh = warp == C::W_FIN ? 0 : NWK / 2;
         uint8_t* __restrict__ Og = a.out + (long long)frame * a.frameOut;
         const int x = x0 + lane;
         for (int bi = OB0, ob = 0; bi < nbur; ++bi, ++ob) {
             RING_WAIT(pkfull + 8 * (ob & 1), (uint32_t)(ob >> 1) & 1u, 4);
-            const uint32_t* pkb = pk + (ob & 1) * 4 * K * TW + lane;
+            const uint32_t* pkb = pk + (ob & 1) * NWK * K * TW + lane;
 #pragma unroll
-            for (int uu = 0; uu < 2; ++uu) {
+            for (int uu = 0; uu < NWK / 2; ++uu) {
                 const int u = fh + uu;
                 const int k = NWK * bi + u - 2 * HALF, y = yb0 + k;
                 if (k < 0 || k >= bhc || x >= a.W) continue;
@@ -401,12 +416,12 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
             const int bs = bi % NB, ob = bi - OB0;
             RING_WAIT(hfull + 8 * bs, (uint32_t)(bi / NB) & 1u, 3);
             if (ob >= 2) RING_WAIT(pkempty + 8 * (ob & 1), (uint32_t)((ob >> 1) - 1) & 1u, 5);
-            uint32_t* pkb = pk + ((ob & 1) * 4 * K + kB) * TW + lane;
+            uint32_t* pkb = pk + ((ob & 1) * NWK * K + kB) * TW + lane;
             const int sn0 = bs * NWK;
-            if (NWK * bi >= WIN && NWK * bi + 3 < nin) {
+            if (NWK * bi >= WIN && NWK * bi + NWK - 1 < nin) {
                 // steady state: every row of the burst has a leaving row and an output row
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < NWK; ++u) {
                     int so = sn0 + u - WIN; if (so < 0) so += NRH;
                     const uint2* Hn = Hk + (sn0 + u) * HROW;
                     const uint2* Ho = Hk + so * HROW;
@@ -415,7 +430,7 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                     pkb[u * K * TW] = keys();
                 }
             } else {
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < NWK; ++u) {
                     const int r = NWK * bi + u;
                     if (r >= nin) break;
                     const uint2* Hn = Hk + (sn0 + u) * HROW;
