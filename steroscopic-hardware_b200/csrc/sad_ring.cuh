@@ -24,6 +24,13 @@
 
 namespace sadgpu {
 
+#ifndef RING_BURST6
+#define RING_BURST6 0             // experiment, off: h >= 12 with bursts of 6 rows, unsplit walks by three warps and a row-granular
+#endif                            // ring release.  Bit-exact but slower (B=31 D=128: 346 vs 253 us): 42 rows leave no slack at h = 15
+                                  // (walkers and consumers wait for each other) and three walker warps are latency-bound.
+#ifndef RING_UNSPLIT4
+#define RING_UNSPLIT4 0           // experiment, off: bursts of 4 rows walked unsplit by two warps (lanes = 16 groups x 2 rows):
+#endif                            // two walker warps are latency-bound (B=31 D=128: 336 vs 253 us)
 #ifndef RING_BURST8_MAX_HALF
 #define RING_BURST8_MAX_HALF 11   // largest h whose ring (window + two bursts of 8 rows of 17 groups) fits shared memory
 #endif
@@ -42,15 +49,19 @@ template <int HALF> struct RingCfg {
     static constexpr int NGS = GT * K;                              // group slots of an H row (>= NGC; the surplus slot is never valid)
     // rows per burst.  17-group rows are small enough for bursts of 8 up to h = 11: the walkers then take whole 32-column rows
     // (lanes = 16 groups x 2 rows) instead of re-warming 16-column halves
-    static constexpr int NWK = (WIDE && HALF <= RING_BURST8_MAX_HALF) ? 8 : 4;
-    static constexpr int WMODE = !WIDE ? 0 : NWK == 4 ? 1 : 2;       // 0: warp = (row, column half); 1: warp = row, half-warps = column halves; 2: warp = row pair, half-warps = rows
+    // h >= 12: bursts of 6 with the ring released row by row (42 rows hold the 2h+1 rows of the window plus two bursts only if a
+    // row is handed back as soon as its last reader is done)
+    static constexpr int NWK = !WIDE ? 4 : HALF <= RING_BURST8_MAX_HALF ? 8 : RING_BURST6 ? 6 : 4;
+    static constexpr bool ROWREL = NWK == 6;                         // h_empty per row instead of per burst
+    static constexpr int WMODE = !WIDE ? 0 : (NWK == 4 && !RING_UNSPLIT4) ? 1 : 2;       // 0: warp = (row, column half); 1: warp = row, half-warps = column halves; 2: warp = row pair, half-warps = rows
     // Ring sizes are multiples of the number of warps that take turns on them (8 walkers; 2 loaders x 4 rows), so that a
     // slot is always produced by the same warp: a parity wait is only sound for a waiter that has seen every phase.
     static constexpr int OB = (WIN + NWK - 1) / NWK;                // a burst has left every window OB bursts later
-    static constexpr int NB = WIDE ? OB + 2 : 6;                    // bursts in the H ring: window + the burst being consumed + the one being written
+    static constexpr int NB = ROWREL ? 7 : WIDE ? OB + 2 : 6;       // bursts in the H ring: window + the burst being consumed + the one being written
     static constexpr int NRH = NB * NWK;                            // H ring rows
-    static constexpr int TR = 16;                                   // pixel-tile ring rows
-    static constexpr int RT = NWK, NSEG = 32 / RT, SEGW = TW / NSEG;  // tail walker: lane = (row of the burst, segment of SEGW columns)
+    static constexpr int TR = NWK == 6 ? 24 : 16;                   // pixel-tile ring rows (a multiple of the burst and of 2 loaders x 4 rows)
+    static constexpr int RT = NWK == 8 ? 8 : 4, NSEG = 32 / RT, SEGW = TW / NSEG;  // tail walker: lane = (row of a pass, segment of SEGW columns)
+    static constexpr int TPASS = (NWK + RT - 1) / RT;               // tail passes per burst
     static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
     static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;
     static constexpr int RW = NGC - 1 + NWALKW;                     // words per aligned-R tile row
@@ -68,12 +79,13 @@ template <int HALF> struct RingCfg {
     static constexpr int NWW = WMODE == 0 ? NWK * 2 : WMODE == 1 ? NWK : NWK / 2;    // walker warps
     static constexpr int TEC = (WMODE == 0 ? 2 : 1) + 1;            // arrivals that free a pixel-tile row: its walker warps + the tail walker
     static constexpr int OB0 = (2 * HALF) / NWK;                    // first burst that holds an output row
-    static constexpr int NBAR = 2 * NB + 2 * TR + 4;
+    static constexpr int NHE = ROWREL ? NRH : NB;                   // h_empty barriers
+    static constexpr int NBAR = NB + NHE + 2 * TR + 4;
     static constexpr int SMEM = OFF_BAR + NBAR * 8;
     static_assert(NGS >= NGC && RT * NSEG == 32 && SEGW % 4 == 0 && W_CONS + K <= W_TAIL && NWW <= W_CONS, "roles");
-    static_assert((NWK == 4 || NWK == 8) && NRH % NWK == 0 && TR % 8 == 0 && TR % NWK == 0, "every ring slot belongs to one producer warp");
+    static_assert((NWK == 4 || NWK == 6 || NWK == 8) && NRH % NWK == 0 && TR % 8 == 0 && TR % NWK == 0, "every ring slot belongs to one producer warp");
     static_assert(SMEM_OK(OFF_BAR), "shared memory");
-    static_assert(NB >= OB + 2, "ring: window bursts + the burst being consumed + the burst being written");
+    static_assert(ROWREL ? NRH + 1 >= WIN + 2 * NWK : NB >= OB + 2, "ring: window + the burst being consumed + the burst being written");
 };
 
 __device__ __forceinline__ void ring_arrive(uint32_t bar)
@@ -161,7 +173,7 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
     uint32_t* pk = reinterpret_cast<uint32_t*>(smem + C::OFF_PK);                // [2][4][K][TW]
     uint8_t* lut = smem + C::OFF_LUT;
     const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(smem + C::OFF_BAR);
-    const uint32_t hfull = bar0, hempty = bar0 + 8 * NB, tfull = bar0 + 16 * NB, tempty = tfull + 8 * TR;
+    const uint32_t hfull = bar0, hempty = bar0 + 8 * NB, tfull = hempty + 8 * C::NHE, tempty = tfull + 8 * TR;
     const uint32_t pkfull = tempty + 8 * TR, pkempty = pkfull + 16;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -182,8 +194,9 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
     if (tid == 0) {
         for (int i = 0; i < NB; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(hfull + 8 * i), "n"(C::NWW + 1));  // walkers + tail walker
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(hempty + 8 * i), "n"(K));
         }
+        for (int i = 0; i < C::NHE; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(hempty + 8 * i), "n"(K));
         for (int i = 0; i < TR; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tfull + 8 * i));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(tempty + 8 * i), "n"(C::TEC));   // walkers + tail walker
@@ -210,39 +223,57 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
         constexpr int HW = TW / C::WSPLIT;
         for (int bi = 0; bi < nbur; ++bi) {
             const int r = NWK * bi + wr, bs = bi % NB;
-            const bool act = r < nin;                          // uniform per warp except in mode 2 (one row per half-warp)
             const int ts = r % TR;
-            if (act) RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
-            if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
-            __syncwarp();
-            if (C::WMODE == 2 || act) {
-                const uint32_t* Lr = Lrep + ts * LW + HW * wh;
-                const uint32_t* Rr = Ral + ts * RW + (NGC - 1 - gl) + (HW / 4) * wh;
-                uint2* Hout = Hs + (bs * NWK + wr) * HROW + gl * TWP + HW * wh;
+            const uint32_t* Lr = Lrep + ts * LW + HW * wh;
+            const uint32_t* Rr = Ral + ts * RW + (NGC - 1 - gl) + (HW / 4) * wh;
+            uint2* Hout = Hs + (bs * NWK + wr) * HROW + gl * TWP + HW * wh;
+            if (C::WMODE != 2) {                               // one row per warp: everything below is warp-uniform
+                if (r < nin) {
+                    RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
+                    if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
+                    if (nvalid >= C::NSTEP) ring_walk<HALF, HW, false>(Lr, Rr, Hout, nvalid - HW * wh, true);
+                    else                    ring_walk<HALF, HW, true>(Lr, Rr, Hout, nvalid - HW * wh, true);
+                    __syncwarp();
+                    if (lane == 0) ring_arrive(tempty + 8 * ts);
+                }
+            } else {                                           // one row per half-warp
+                const bool act = r < nin;
+                if (act) RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
+                if (C::ROWREL) { if (act && r >= NRH) RING_WAIT(hempty + 8 * (r % NRH), (uint32_t)(r / NRH - 1) & 1u, 1); }
+                else if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
+                __syncwarp();
                 if (nvalid >= C::NSTEP) ring_walk<HALF, HW, false>(Lr, Rr, Hout, nvalid - HW * wh, act);
                 else                    ring_walk<HALF, HW, true>(Lr, Rr, Hout, nvalid - HW * wh, act);
+                __syncwarp();
+                if (act && (lane & 15) == 0) ring_arrive(tempty + 8 * ts);
             }
-            __syncwarp();
-            if (act && (lane == 0 || (C::WMODE == 2 && lane == 16))) ring_arrive(tempty + 8 * ts);
             if (lane == 0) ring_arrive(hfull + 8 * bs);
         }
     } else if (warp == C::W_TAIL) {
-        // ---- tail walker: group NGC-1 of the rows of a burst; lane = (row j, segment s of SEGW columns) ----
-        const int j = lane / C::NSEG, s = lane % C::NSEG;
+        // ---- tail walker: group NGC-1 of the rows of a burst, RT rows per pass; lane = (row j, segment s of SEGW columns) ----
+        const int j0 = lane / C::NSEG, s = lane % C::NSEG;
         for (int bi = 0; bi < nbur; ++bi) {
-            const int r = NWK * bi + j, bs = bi % NB;
-            const bool act = r < nin;
-            const int ts = r % TR;
-            if (act) RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
-            if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
-            __syncwarp();
-            const uint32_t* Lr = Lrep + ts * LW + C::SEGW * s;
-            const uint32_t* Rr = Ral + ts * RW + (C::SEGW / 4) * s;
-            uint2* Hout = Hs + (bs * NWK + j) * HROW + (NGC - 1) * TWP + C::SEGW * s;
-            if (nvalid >= C::NSTEP) ring_walk<HALF, C::SEGW, false>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
-            else                    ring_walk<HALF, C::SEGW, true>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
-            __syncwarp();
-            if (act && s == 0) ring_arrive(tempty + 8 * ts);
+            const int bs = bi % NB;
+#pragma unroll
+            for (int pass = 0; pass < C::TPASS; ++pass) {
+                const int j = j0 + C::RT * pass;
+                const int r = NWK * bi + j;
+                const bool act = (C::TPASS == 1 || j < NWK) && r < nin;
+                const int ts = r % TR;
+                if (act) {
+                    RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
+                    if (C::ROWREL && r >= NRH) RING_WAIT(hempty + 8 * (r % NRH), (uint32_t)(r / NRH - 1) & 1u, 1);
+                }
+                if (!C::ROWREL && pass == 0 && bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
+                __syncwarp();
+                const uint32_t* Lr = Lrep + ts * LW + C::SEGW * s;
+                const uint32_t* Rr = Ral + ts * RW + (C::SEGW / 4) * s;
+                uint2* Hout = Hs + (bs * NWK + ((C::TPASS == 1 || j < NWK) ? j : 0)) * HROW + (NGC - 1) * TWP + C::SEGW * s;
+                if (nvalid >= C::NSTEP) ring_walk<HALF, C::SEGW, false>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
+                else                    ring_walk<HALF, C::SEGW, true>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
+                __syncwarp();
+                if (act && s == 0) ring_arrive(tempty + 8 * ts);
+            }
             if (lane == 0) ring_arrive(hfull + 8 * bs);
         }
     } else if (warp == C::W_LD0 || warp == C::W_LD1) {
@@ -427,6 +458,7 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                     const uint2* Ho = Hk + so * HROW;
 #pragma unroll
                     for (int j = 0; j < GT; ++j) update(j, Hn[j * TWP], Ho[j * TWP]);
+                    if (C::ROWREL) { __syncwarp(); if (lane == 0) ring_arrive(hempty + 8 * so); }     // the leaving row is free at once
                     pkb[u * K * TW] = keys();
                 }
             } else {
@@ -438,12 +470,13 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                     const uint2* Ho = Hk + so * HROW;
 #pragma unroll
                     for (int j = 0; j < GT; ++j) update(j, Hn[j * TWP], r >= WIN ? Ho[j * TWP] : make_uint2(0u, 0u));
+                    if (C::ROWREL && r >= WIN) { __syncwarp(); if (lane == 0) ring_arrive(hempty + 8 * so); }
                     if (r >= 2 * HALF) pkb[u * K * TW] = keys();
                 }
             }
             __syncwarp();
             if (lane == 0) {
-                if (bi >= OB) ring_arrive(hempty + 8 * ((bi - OB) % NB));       // burst bi-OB has left every window
+                if (!C::ROWREL && bi >= OB) ring_arrive(hempty + 8 * ((bi - OB) % NB));      // burst bi-OB has left every window
                 if (ob >= 0) ring_arrive(pkfull + 8 * (ob & 1));
             }
         }
