@@ -24,6 +24,12 @@
 
 namespace sadgpu {
 
+#ifndef RING_WIDE_SLACK
+#define RING_WIDE_SLACK 0         // extra bursts of ring slack in the 17-group instances where shared memory allows
+#endif
+#ifndef RING_PKATOM
+#define RING_PKATOM 1
+#endif
 #ifndef RING_BURST6
 #define RING_BURST6 0             // experiment, off: h >= 12 with bursts of 6 rows, unsplit walks by three warps and a row-granular
 #endif                            // ring release.  Bit-exact but slower (B=31 D=128: 346 vs 253 us): 42 rows leave no slack at h = 15
@@ -32,7 +38,7 @@ namespace sadgpu {
 #define RING_UNSPLIT4 0           // experiment, off: bursts of 4 rows walked unsplit by two warps (lanes = 16 groups x 2 rows):
 #endif                            // two walker warps are latency-bound (B=31 D=128: 336 vs 253 us)
 #ifndef RING_BURST8_MAX_HALF
-#define RING_BURST8_MAX_HALF 11   // largest h whose ring (window + two bursts of 8 rows of 17 groups) fits shared memory
+#define RING_BURST8_MAX_HALF 15   // largest h whose ring (window + two bursts of 8 rows of 17 groups) fits shared memory (11 without RING_PKATOM)
 #endif
 constexpr bool SMEM_OK(int bytes) { return bytes + 1024 <= 232448; }
 
@@ -52,12 +58,17 @@ template <int HALF> struct RingCfg {
     // h >= 12: bursts of 6 with the ring released row by row (42 rows hold the 2h+1 rows of the window plus two bursts only if a
     // row is handed back as soon as its last reader is done)
     static constexpr int NWK = !WIDE ? 4 : HALF <= RING_BURST8_MAX_HALF ? 8 : RING_BURST6 ? 6 : 4;
+    // 17-group instances: the consumers fold their partial keys into ONE word per pixel with a shared-memory atomicMin instead
+    // of K words that the finishers reduce, and an H row holds exactly 17 group slots (the ninth consumer's second slot reads
+    // into the next row; its keys are invalid by construction).  That frees 25 KB: room for a ring of 8-row bursts up to h = 15.
+    static constexpr bool PKATOM = WIDE && RING_PKATOM;
+    static constexpr int PKK = PKATOM ? 1 : K;                      // words per pixel and row in pk
     static constexpr bool ROWREL = NWK == 6;                         // h_empty per row instead of per burst
     static constexpr int WMODE = !WIDE ? 0 : (NWK == 4 && !RING_UNSPLIT4) ? 1 : 2;       // 0: warp = (row, column half); 1: warp = row, half-warps = column halves; 2: warp = row pair, half-warps = rows
     // Ring sizes are multiples of the number of warps that take turns on them (8 walkers; 2 loaders x 4 rows), so that a
     // slot is always produced by the same warp: a parity wait is only sound for a waiter that has seen every phase.
     static constexpr int OB = (WIN + NWK - 1) / NWK;                // a burst has left every window OB bursts later
-    static constexpr int NB = ROWREL ? 7 : WIDE ? OB + 2 : 6;       // bursts in the H ring: window + the burst being consumed + the one being written
+    static constexpr int NB = ROWREL ? 7 : WIDE ? OB + 2 + (HALF <= 11 ? RING_WIDE_SLACK : 0) : 6;   // bursts in the H ring: window + the burst being consumed + the one being written (+ slack)
     static constexpr int NRH = NB * NWK;                            // H ring rows
     static constexpr int TR = NWK == 6 ? 24 : 16;                   // pixel-tile ring rows (a multiple of the burst and of 2 loaders x 4 rows)
     static constexpr int RT = NWK == 8 ? 8 : 4, NSEG = 32 / RT, SEGW = TW / NSEG;  // tail walker: lane = (row of a pass, segment of SEGW columns)
@@ -65,15 +76,15 @@ template <int HALF> struct RingCfg {
     static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
     static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;
     static constexpr int RW = NGC - 1 + NWALKW;                     // words per aligned-R tile row
-    static constexpr int HROW = NGS * TWP;                          // uint2 per H row
+    static constexpr int HROW = (PKATOM ? NGC : NGS) * TWP;         // uint2 per H row
     static constexpr int NT = 768;
     // warp roles; SM sub-partition = warp % 4
     static constexpr int W_CONS = 8, W_TAIL = 19, W_FIN = 20, W_LD0 = 21, W_LD1 = 22, W_FIN2 = 23;
-    static constexpr int H_BYTES = NRH * HROW * 8;
+    static constexpr int H_BYTES = (NRH * HROW + (NGS - NGC) * TWP) * 8;    // + the surplus slot of the last row
     static constexpr int OFF_L = ((H_BYTES + 15) / 16) * 16;
     static constexpr int OFF_R = OFF_L + TR * LW * 4;
-    static constexpr int OFF_PK = OFF_R + TR * RW * 4;              // [2][NWK][K][TW]
-    static constexpr int OFF_LUT = OFF_PK + 2 * NWK * K * TW * 4;
+    static constexpr int OFF_PK = OFF_R + TR * RW * 4;              // [2][NWK][PKK][TW]
+    static constexpr int OFF_LUT = OFF_PK + 2 * NWK * PKK * TW * 4;
     static constexpr int OFF_BAR = ((OFF_LUT + 1040 + 7) / 8) * 8;
     static constexpr int WSPLIT = WMODE == 2 ? 1 : 2;               // column segments of a row walk
     static constexpr int NWW = WMODE == 0 ? NWK * 2 : WMODE == 1 ? NWK : NWK / 2;    // walker warps
@@ -191,6 +202,7 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
     const int nbur = (nin + NWK - 1) / NWK;                   // bursts of NWK rows
 
     for (int d = tid; d < 1040; d += C::NT) lut[d] = d <= a.D ? (uint8_t)((d * 255) / a.D) : 0;
+    if (C::PKATOM) for (int i = tid; i < 2 * NWK * TW; i += C::NT) pk[i] = 0xFFFFFFFFu;
     if (tid == 0) {
         for (int i = 0; i < NB; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(hfull + 8 * i), "n"(C::NWW + 1));  // walkers + tail walker
@@ -371,15 +383,18 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
         const int x = x0 + lane;
         for (int bi = OB0, ob = 0; bi < nbur; ++bi, ++ob) {
             RING_WAIT(pkfull + 8 * (ob & 1), (uint32_t)(ob >> 1) & 1u, 4);
-            const uint32_t* pkb = pk + (ob & 1) * NWK * K * TW + lane;
+            uint32_t* pkb = pk + (ob & 1) * NWK * C::PKK * TW + lane;
 #pragma unroll
             for (int uu = 0; uu < NWK / 2; ++uu) {
                 const int u = fh + uu;
                 const int k = NWK * bi + u - 2 * HALF, y = yb0 + k;
                 if (k < 0 || k >= bhc || x >= a.W) continue;
                 uint32_t best = 0xFFFFFFFFu;
+                if (C::PKATOM) { best = pkb[u * TW]; pkb[u * TW] = 0xFFFFFFFFu; }     // read and re-arm for the burst after next
+                else {
 #pragma unroll
-                for (int kk = 0; kk < K; ++kk) best = min(best, pkb[(u * K + kk) * TW]);
+                    for (int kk = 0; kk < K; ++kk) best = min(best, pkb[(u * K + kk) * TW]);
+                }
                 if (x < HALF) best = 0;                      // sad.go:212-218: both windows clamp, d = 0 wins
                 if (a.NC == 1) Og[(size_t)y * a.pitchOut + x] = lut[best & (C::WIDE ? 511u : 0xFFFFu)];
                 else atomicMin(a.gkey + ((size_t)frame * a.H + y) * a.W + x,
@@ -447,7 +462,11 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
             const int bs = bi % NB, ob = bi - OB0;
             RING_WAIT(hfull + 8 * bs, (uint32_t)(bi / NB) & 1u, 3);
             if (ob >= 2) RING_WAIT(pkempty + 8 * (ob & 1), (uint32_t)((ob >> 1) - 1) & 1u, 5);
-            uint32_t* pkb = pk + ((ob & 1) * NWK * K + kB) * TW + lane;
+            uint32_t* pkb = pk + ((ob & 1) * NWK * C::PKK + (C::PKATOM ? 0 : kB)) * TW + lane;
+            auto emit = [&](int u, uint32_t key) {
+                if (C::PKATOM) atomicMin(pkb + u * TW, key);
+                else pkb[u * K * TW] = key;
+            };
             const int sn0 = bs * NWK;
             if (NWK * bi >= WIN && NWK * bi + NWK - 1 < nin) {
                 // steady state: every row of the burst has a leaving row and an output row
@@ -459,7 +478,7 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
 #pragma unroll
                     for (int j = 0; j < GT; ++j) update(j, Hn[j * TWP], Ho[j * TWP]);
                     if (C::ROWREL) { __syncwarp(); if (lane == 0) ring_arrive(hempty + 8 * so); }     // the leaving row is free at once
-                    pkb[u * K * TW] = keys();
+                    emit(u, keys());
                 }
             } else {
                 for (int u = 0; u < NWK; ++u) {
@@ -471,7 +490,7 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
 #pragma unroll
                     for (int j = 0; j < GT; ++j) update(j, Hn[j * TWP], r >= WIN ? Ho[j * TWP] : make_uint2(0u, 0u));
                     if (C::ROWREL && r >= WIN) { __syncwarp(); if (lane == 0) ring_arrive(hempty + 8 * so); }
-                    if (r >= 2 * HALF) pkb[u * K * TW] = keys();
+                    if (r >= 2 * HALF) emit(u, keys());
                 }
             }
             __syncwarp();

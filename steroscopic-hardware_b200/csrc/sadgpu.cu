@@ -298,13 +298,13 @@ const FastEntry kRing[11] = {ring_entry<5>(), ring_entry<6>(), ring_entry<7>(), 
                              ring_entry<11>(), ring_entry<12>(), ring_entry<13>(), ring_entry<14>(), ring_entry<15>()};
 bool ring_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
 // Planner default, from the measured variant sweep (profiles/r01_variant_sweep.json): a ring pass over 33 (17) groups costs about
-// 1.65x (1.7x) a pass of the phase-alternating kernels over 18 (8) groups, so the ring kernel wins whenever it needs fewer passes.
+// 1.65x (1.5x) a pass of the phase-alternating kernels over 18 (8) groups, so the ring kernel wins whenever it needs fewer passes.
 bool ring_auto(int B, int D)
 {
     if (!ring_supported(B)) return false;
     const int ng = (D + 4) / 4;
     if (B / 2 <= 7) return 165 * ((ng + 32) / 33) < 100 * ((ng + 17) / 18);
-    return 170 * ((ng + 16) / 17) < 100 * ((ng + 7) / 8);
+    return 149 * ((ng + 16) / 17) < 100 * ((ng + 7) / 8);
 }   // faster than the register-ring fast path from 19 groups on (profiles/)
 
 bool vh_auto(int B, int D) { (void)B; (void)D; return false; }      // planner default: decided by measurement (profiles/)
