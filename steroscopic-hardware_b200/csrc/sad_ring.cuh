@@ -24,6 +24,11 @@
 
 namespace sadgpu {
 
+#ifndef RING_SPLIT8_MIN_HALF
+#define RING_SPLIT8_MIN_HALF 15   // from this h on, bursts of 8 rows are walked by eight warps (half-warps = column halves) instead of four
+                                  // (half-warps = rows): +48 % walker instructions but half the walk latency.  Measured: h = 15 5 % faster
+                                  // (216 -> 205 us at B=31 D=128), h = 8..12 unchanged or 1 % slower
+#endif
 #ifndef RING_WIDE_SLACK
 #define RING_WIDE_SLACK 0         // extra bursts of ring slack in the 17-group instances where shared memory allows
 #endif
@@ -64,7 +69,7 @@ template <int HALF> struct RingCfg {
     static constexpr bool PKATOM = WIDE && RING_PKATOM;
     static constexpr int PKK = PKATOM ? 1 : K;                      // words per pixel and row in pk
     static constexpr bool ROWREL = NWK == 6;                         // h_empty per row instead of per burst
-    static constexpr int WMODE = !WIDE ? 0 : (NWK == 4 && !RING_UNSPLIT4) ? 1 : 2;       // 0: warp = (row, column half); 1: warp = row, half-warps = column halves; 2: warp = row pair, half-warps = rows
+    static constexpr int WMODE = !WIDE ? 0 : ((NWK == 4 && !RING_UNSPLIT4) || (NWK == 8 && HALF >= RING_SPLIT8_MIN_HALF)) ? 1 : 2;       // 0: warp = (row, column half); 1: warp = row, half-warps = column halves; 2: warp = row pair, half-warps = rows
     // Ring sizes are multiples of the number of warps that take turns on them (8 walkers; 2 loaders x 4 rows), so that a
     // slot is always produced by the same warp: a parity wait is only sound for a waiter that has seen every phase.
     static constexpr int OB = (WIN + NWK - 1) / NWK;                // a burst has left every window OB bursts later
