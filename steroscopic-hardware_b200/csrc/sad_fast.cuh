@@ -155,19 +155,29 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
     const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;   // aligned origin of the R tile (multiple of 4)
     const int nvalid = a.W - (x0 - HALF);
 
-    auto load_tiles = [&](int rbase) {
-        for (int idx = tid; idx < RB * C::LW; idx += NT) {
+    // Tile loads are split in two: the global loads of the next batch are issued into registers at the start of phase B and
+    // written to shared memory at its end, so that their latency (HBM when the frames stream) overlaps phase B.
+    constexpr int NLE = (RB * C::LW + NT - 1) / NT, NRE = (RB * C::RW + NT - 1) / NT;
+    static_assert(NLE <= 4, "left pixels of a thread are packed into one register");
+    uint32_t tl = 0, tr[NRE];
+    auto issue_tiles = [&](int rbase) {
+        tl = 0;
+#pragma unroll
+        for (int q = 0; q < NLE; ++q) {
+            const int idx = tid + q * NT;
             const int rb = idx / C::LW, i = idx - rb * C::LW;
             const int y = rbase + rb, x = x0 - HALF + i;
             uint32_t v = 0;
-            if ((unsigned)y < (unsigned)a.H && (unsigned)x < (unsigned)a.W) v = Lg[(size_t)y * a.pitchL + x];
-            Lrep[idx] = v * 0x01010101u;
+            if (idx < RB * C::LW && (unsigned)y < (unsigned)a.H && (unsigned)x < (unsigned)a.W) v = Lg[(size_t)y * a.pitchL + x];
+            tl |= v << (8 * q);
         }
-        for (int idx = tid; idx < RB * C::RW; idx += NT) {
+#pragma unroll
+        for (int q = 0; q < NRE; ++q) {
+            const int idx = tid + q * NT;
             const int rb = idx / C::RW, j = idx - rb * C::RW;
             const int y = rbase + rb, x = xr0 + 4 * j;
             uint32_t v = 0;
-            if ((unsigned)y < (unsigned)a.H && x + 3 >= 0 && x < a.W) {
+            if (idx < RB * C::RW && (unsigned)y < (unsigned)a.H && x + 3 >= 0 && x < a.W) {
                 const uint8_t* p = Rg + (size_t)y * a.pitchR;
                 if (a.aligned && x >= 0 && x + 3 < a.W) v = *reinterpret_cast<const uint32_t*>(p + x);
                 else {
@@ -176,8 +186,14 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
                         if ((unsigned)(x + b) < (unsigned)a.W) v |= (uint32_t)p[x + b] << (8 * b);
                 }
             }
-            Ral[idx] = v;
+            tr[q] = v;
         }
+    };
+    auto commit_tiles = [&]() {
+#pragma unroll
+        for (int q = 0; q < NLE; ++q) { const int idx = tid + q * NT; if (idx < RB * C::LW) Lrep[idx] = ((tl >> (8 * q)) & 0xFFu) * 0x01010101u; }
+#pragma unroll
+        for (int q = 0; q < NRE; ++q) { const int idx = tid + q * NT; if (idx < RB * C::RW) Ral[idx] = tr[q]; }
     };
 
     auto phaseC = [&](int batch) {
@@ -198,7 +214,7 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
         }
     };
 
-    load_tiles(r0);
+    issue_tiles(r0); commit_tiles();
     __syncthreads();
     for (int batch = 0; batch < nbatches; ++batch) {
         const int rbase = r0 + batch * RB;
@@ -214,7 +230,8 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
         }
         __syncthreads();
         // ---- phase B (and the tile load of the next batch) ----
-        if (batch + 1 < nbatches) load_tiles(rbase + RB);
+        // h >= 6: the register ring leaves no room for loads in flight across phase B (they would spill): load and store at once
+        if (batch + 1 < nbatches) { issue_tiles(rbase + RB); if (HALF >= 6) commit_tiles(); }
         {
             const uint2* Hp = Hs + (kB * GT) * TWP + xlB;
 #pragma unroll
@@ -244,6 +261,7 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
                 }
             }
         }
+        if (HALF < 6 && batch + 1 < nbatches) commit_tiles();   // phase A of this batch is behind the barrier above: the tiles are free
         __syncthreads();
     }
     phaseC(nbatches - 1);

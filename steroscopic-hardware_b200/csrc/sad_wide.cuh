@@ -121,19 +121,27 @@ __global__ void __launch_bounds__(WideCfg<HALF>::NT, 1) sad_wide_kernel(const Fa
     const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;
     const int nvalid = a.W - (x0 - HALF);
 
-    auto load_tiles = [&](int rbase) {
-        for (int idx = tid; idx < RB * C::LW; idx += NT) {
+    // Tile loads are split in two: the global loads of the next batch are issued into registers at the start of phase B and
+    // written to shared memory at its end, so that their latency (HBM when the frames stream) overlaps phase B.
+    constexpr int NLE = (RB * C::LW + NT - 1) / NT, NRE = (RB * C::RW + NT - 1) / NT;
+    uint32_t tl[NLE], tr[NRE];
+    auto issue_tiles = [&](int rbase) {
+#pragma unroll
+        for (int q = 0; q < NLE; ++q) {
+            const int idx = tid + q * NT;
             const int rb = idx / C::LW, i = idx - rb * C::LW;
             const int y = rbase + rb, x = x0 - HALF + i;
             uint32_t v = 0;
-            if ((unsigned)y < (unsigned)a.H && (unsigned)x < (unsigned)a.W) v = Lg[(size_t)y * a.pitchL + x];
-            Lrep[idx] = v * 0x01010101u;
+            if (idx < RB * C::LW && (unsigned)y < (unsigned)a.H && (unsigned)x < (unsigned)a.W) v = Lg[(size_t)y * a.pitchL + x];
+            tl[q] = v;
         }
-        for (int idx = tid; idx < RB * C::RW; idx += NT) {
+#pragma unroll
+        for (int q = 0; q < NRE; ++q) {
+            const int idx = tid + q * NT;
             const int rb = idx / C::RW, j = idx - rb * C::RW;
             const int y = rbase + rb, x = xr0 + 4 * j;
             uint32_t v = 0;
-            if ((unsigned)y < (unsigned)a.H && x + 3 >= 0 && x < a.W) {
+            if (idx < RB * C::RW && (unsigned)y < (unsigned)a.H && x + 3 >= 0 && x < a.W) {
                 const uint8_t* p = Rg + (size_t)y * a.pitchR;
                 if (a.aligned && x >= 0 && x + 3 < a.W) v = *reinterpret_cast<const uint32_t*>(p + x);
                 else {
@@ -142,8 +150,14 @@ __global__ void __launch_bounds__(WideCfg<HALF>::NT, 1) sad_wide_kernel(const Fa
                         if ((unsigned)(x + b) < (unsigned)a.W) v |= (uint32_t)p[x + b] << (8 * b);
                 }
             }
-            Ral[idx] = v;
+            tr[q] = v;
         }
+    };
+    auto commit_tiles = [&]() {
+#pragma unroll
+        for (int q = 0; q < NLE; ++q) { const int idx = tid + q * NT; if (idx < RB * C::LW) Lrep[idx] = tl[q] * 0x01010101u; }
+#pragma unroll
+        for (int q = 0; q < NRE; ++q) { const int idx = tid + q * NT; if (idx < RB * C::RW) Ral[idx] = tr[q]; }
     };
 
     auto phaseC = [&](int batch) {
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__(WideCfg<HALF>::NT, 1) sad_wide_kernel(const Fa
         }
     };
 
-    load_tiles(r0);
+    issue_tiles(r0); commit_tiles();
     __syncthreads();
     int slot0 = 0;                                               // ring slot of the first row of the current batch
     for (int batch = 0; batch < nbatches; ++batch) {
@@ -180,7 +194,7 @@ __global__ void __launch_bounds__(WideCfg<HALF>::NT, 1) sad_wide_kernel(const Fa
         }
         __syncthreads();
         // ---- phase B (and the tile load of the next batch) ----
-        if (batch + 1 < nbatches) load_tiles(rbase + RB);
+        if (batch + 1 < nbatches) issue_tiles(rbase + RB);
         {
             int sn = slot0;                                      // slot of the entering row
             int so = slot0 - WIN; if (so < 0) so += NRS;         // slot of the leaving row (2h+1 rows behind)
@@ -216,6 +230,7 @@ __global__ void __launch_bounds__(WideCfg<HALF>::NT, 1) sad_wide_kernel(const Fa
             }
         }
         slot0 += RB; if (slot0 >= NRS) slot0 -= NRS;
+        if (batch + 1 < nbatches) commit_tiles();          // phase A of this batch is behind the barrier above: the tiles are free
         __syncthreads();
     }
     phaseC(nbatches - 1);

@@ -297,17 +297,18 @@ bool vh_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
 const FastEntry kRing[11] = {ring_entry<5>(), ring_entry<6>(), ring_entry<7>(), ring_entry<8>(), ring_entry<9>(), ring_entry<10>(),
                              ring_entry<11>(), ring_entry<12>(), ring_entry<13>(), ring_entry<14>(), ring_entry<15>()};
 bool ring_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
-// Planner default, from the measured variant sweep (profiles/r01_variant_sweep.json): a ring pass over 33 (17) groups costs about
-// 1.65x (1.5x) a pass of the phase-alternating kernels over 18 (8) groups, so the ring kernel wins whenever it needs fewer passes.
+// Planner default, from the measured variant sweep (profiles/r01_variant_sweep.json, inputs streaming from HBM): a ring pass over
+// 33 groups costs 1.73x (block 10, 11) or 1.45x (block 12..15) a pass of the phase-alternating kernel over 18 groups, a ring pass over
+// 17 groups 1.95x a pass of the wide kernel over 8 groups; the ring kernel is chosen whenever its passes are cheaper in total.
 bool ring_auto(int B, int D)
 {
     if (!ring_supported(B)) return false;
     const int ng = (D + 4) / 4;
-    if (B / 2 <= 7) return 165 * ((ng + 32) / 33) < 100 * ((ng + 17) / 18);
-    return 149 * ((ng + 16) / 17) < 100 * ((ng + 7) / 8);
-}   // faster than the register-ring fast path from 19 groups on (profiles/)
+    if (B / 2 <= 7) return (B / 2 == 5 ? 173 : 145) * ((ng + 32) / 33) < 100 * ((ng + 17) / 18);
+    return 195 * ((ng + 16) / 17) < 100 * ((ng + 7) / 8);
+}
 
-bool vh_auto(int B, int D) { (void)B; (void)D; return false; }      // planner default: decided by measurement (profiles/)
+bool vh_auto(int B, int D) { (void)B; (void)D; return false; }      // never the fastest variant (profiles/r01_variant_sweep.json)
 
 bool fast_supported(int B) { return B / 2 <= 7; }
 bool wide_supported(int B) { return B / 2 >= 8 && B / 2 <= 15; }
