@@ -298,13 +298,13 @@ const FastEntry kRing[11] = {ring_entry<5>(), ring_entry<6>(), ring_entry<7>(), 
                              ring_entry<11>(), ring_entry<12>(), ring_entry<13>(), ring_entry<14>(), ring_entry<15>()};
 bool ring_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
 // Planner default, from the measured variant sweep (profiles/r01_variant_sweep.json, inputs streaming from HBM): a ring pass over
-// 33 groups costs 1.73x (block 10, 11) or 1.45x (block 12..15) a pass of the phase-alternating kernel over 18 groups, a ring pass over
+// 33 groups costs about 1.7x a pass of the phase-alternating kernel over 18 groups, a ring pass over
 // 17 groups 1.95x a pass of the wide kernel over 8 groups; the ring kernel is chosen whenever its passes are cheaper in total.
 bool ring_auto(int B, int D)
 {
     if (!ring_supported(B)) return false;
     const int ng = (D + 4) / 4;
-    if (B / 2 <= 7) return (B / 2 == 5 ? 173 : 145) * ((ng + 32) / 33) < 100 * ((ng + 17) / 18);
+    if (B / 2 <= 7) return 172 * ((ng + 32) / 33) < 100 * ((ng + 17) / 18);
     return 195 * ((ng + 16) / 17) < 100 * ((ng + 7) / 8);
 }
 
