@@ -126,8 +126,10 @@ int  sadgpu_reserve_batch(sadgpu_ctx *ctx, int max_frames);
 int  sadgpu_submit_batch_into(sadgpu_ctx *ctx, int stream, int n_frames, const uint8_t *pairs, int w, int h,
                               int block_size, int max_disparity, uint8_t *out, uint64_t *ticket);
 
-/* One frame split into row bands with a block_size/2 halo over ALL devices of the context
- * (one band per device, streams 0..n_devices-1), host-side gather into out. */
+/* One frame split into row bands with a block_size/2 halo over ALL devices of the context, host-side gather into out.
+ * Band i runs on stream i (device i % n_devices); a context with spare streams uses up to four bands per device, so that
+ * the upload of a band overlaps the kernel of the previous one — also the lowest-latency way to run ONE large frame on ONE
+ * device (streams 0..n-1 must be idle). */
 int  sadgpu_compute_sharded(sadgpu_ctx *ctx,
                             const uint8_t *left, int left_stride, const uint8_t *right, int right_stride,
                             int w, int h, int block_size, int max_disparity,

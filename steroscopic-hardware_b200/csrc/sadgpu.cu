@@ -1015,23 +1015,30 @@ int sadgpu_compute_sharded(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_
                            int w, int h, int B, int D, uint8_t* out, int out_stride)
 {
     if (!c) return SADGPU_EINVAL;
-    const int n = (int)std::min(c->devices.size(), c->slots.size());
+    // one band per device; with spare streams up to four bands per device, so that on each device the upload of a band
+    // overlaps the kernel of the previous one (stream s lives on device s % n_devices)
+    const int n = (int)std::min(c->slots.size(), c->devices.size() * 4);
     int rc = check_io(c, 0, l, ls, r, rs, w, h);
     if (rc) return rc;
     if (!out || out_stride < w) return SADGPU_EINVAL;
     if ((rc = validate(w, h, B, D, 0, h))) return rc;
-    std::vector<uint64_t> tk(n, 0);
+    const bool direct = in_pool(c, out, (size_t)(h - 1) * out_stride + w);      // pinned destination: the D2H copies land in it
     std::vector<int> started(n, 0);
     int first_err = 0;
-    for (int i = 0; i < n; ++i) {                       // row band i -> device i, halo handled by submit
+    for (int i = 0; i < n; ++i) {                       // row band i -> stream i, halo handled by the upload
         const int y0 = (int)((long)h * i / n), y1 = (int)((long)h * (i + 1) / n);
-        rc = sadgpu_submit(c, i, l, ls, r, rs, w, h, B, D, y0, y1, &tk[i]);
-        if (rc) { first_err = rc; break; }
+        Slot* s = c->slots[i];
+        std::lock_guard<std::mutex> g(s->mu);
+        if (s->busy) { first_err = SADGPU_EBUSY; break; }
+        rc = submit_locked(c, s, l, ls, r, rs, w, h, B, D, y0, y1, direct ? out : nullptr, out_stride);
+        if (rc) { cudaStreamSynchronize(s->st); s->busy = false; first_err = rc; break; }
         started[i] = 1;
     }
     for (int i = 0; i < n; ++i) {                       // host-side gather: disjoint rows of one Pix
         if (!started[i]) continue;
-        rc = sadgpu_wait(c, tk[i], out, out_stride);
+        Slot* s = c->slots[i];
+        std::lock_guard<std::mutex> g(s->mu);
+        rc = wait_locked(c, s, out, out_stride);
         if (rc && !first_err) first_err = rc;
     }
     return first_err;
