@@ -1,7 +1,7 @@
 """Developer battery: GPU path vs oracle on many small cases + the fixtures.  Run on the GPU box:
    python tools/gpu_check.py [--quick]"""
 import os, sys, time, json
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "steroscopic-hardware_b200"))
 import numpy as np
 import torch

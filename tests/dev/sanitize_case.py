@@ -1,6 +1,6 @@
 """Small invocation of every kernel variant for compute-sanitizer (memcheck / racecheck)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "steroscopic-hardware_b200"))
 import numpy as np, torch, despair
 from oracle import oracle as O

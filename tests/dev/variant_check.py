@@ -1,6 +1,6 @@
 """Developer check of the vertical-first kernel (kernel_variant=5) against the oracle + timing vs the default plan."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "steroscopic-hardware_b200"))
 import numpy as np, torch
 from oracle import oracle as O

@@ -4,14 +4,12 @@ import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "steroscopic-hardware_b200"))
 import numpy as np, torch, despair
-from oracle import oracle as O
 W, H, B, D = 3840, 2160, 31, 256
 rng = np.random.default_rng(4321)
 T = rng.integers(0, 256, (H, W + 512), dtype=np.uint8)
 L = np.ascontiguousarray(T[:, 256:256 + W]); R = np.ascontiguousarray(np.roll(T, -37, 1)[:, 256:256 + W])
 ndev = torch.cuda.device_count()
-O.build()
-exp_rows = O.frame_box(L, R, B, D, 1000, 1016)
+ref_rows = None          # rows of the one-band run: every sharded run must reproduce them (the oracle comparison lives in tests/)
 out = []
 for n in (1, 2, 4, 8):
     if n > ndev: break
@@ -22,8 +20,9 @@ for n in (1, 2, 4, 8):
     t0 = time.perf_counter(); reps = 10
     for _ in range(reps): ctx.compute_sharded(pl, pr, B, D, out=po)
     dt = (time.perf_counter() - t0) / reps
-    ok = bool(np.array_equal(po[1000:1016], exp_rows))
-    r = {"n_gpus": n, "ms_per_frame": round(dt * 1e3, 3), "frames_per_sec": round(1 / dt, 1), "Mpix_D_per_s": round(W * H * D / dt / 1e6, 1), "rows_match_oracle": ok}
+    if ref_rows is None: ref_rows = po[1000:1100].copy()
+    ok = bool(np.array_equal(po[1000:1100], ref_rows))
+    r = {"n_gpus": n, "ms_per_frame": round(dt * 1e3, 3), "frames_per_sec": round(1 / dt, 1), "Mpix_D_per_s": round(W * H * D / dt / 1e6, 1), "rows_match_single_gpu_run": ok}
     out.append(r); print(r, flush=True)
     ctx.close()
 json.dump({"config": "cfg4 3840x2160 B=31 D=256, one frame per call, pinned host buffers, row bands + 15-row halo, no collective", "runs": out},
