@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
     // written to shared memory at its end, so that their latency (HBM when the frames stream) overlaps phase B.
     constexpr int NLE = (RB * C::LW + NT - 1) / NT, NRE = (RB * C::RW + NT - 1) / NT;
     static_assert(NLE <= 4, "left pixels of a thread are packed into one register");
+    constexpr bool ASYNC_R = HALF >= 6;       // the register ring of h = 6, 7 leaves no room for right words in flight: cp.async instead
     uint32_t tl = 0, tr[NRE];
     auto issue_tiles = [&](int rbase) {
         tl = 0;
@@ -177,23 +178,34 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
             const int rb = idx / C::RW, j = idx - rb * C::RW;
             const int y = rbase + rb, x = xr0 + 4 * j;
             uint32_t v = 0;
+            bool async = false;
             if (idx < RB * C::RW && (unsigned)y < (unsigned)a.H && x + 3 >= 0 && x < a.W) {
                 const uint8_t* p = Rg + (size_t)y * a.pitchR;
-                if (a.aligned && x >= 0 && x + 3 < a.W) v = *reinterpret_cast<const uint32_t*>(p + x);
-                else {
+                if (a.aligned && x >= 0 && x + 3 < a.W) {
+                    if (ASYNC_R) {          // no register is held across phase B: the word goes straight to shared memory
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(Ral + idx)), "l"(p + x) : "memory");
+                        async = true;
+                    } else v = *reinterpret_cast<const uint32_t*>(p + x);
+                } else {
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
                         if ((unsigned)(x + b) < (unsigned)a.W) v |= (uint32_t)p[x + b] << (8 * b);
                 }
             }
-            tr[q] = v;
+            if (ASYNC_R) { if (!async && idx < RB * C::RW) Ral[idx] = v; }      // borders and zero rows: stored at once (the tiles are free during phase B)
+            else tr[q] = v;
         }
+        if (ASYNC_R) asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto commit_tiles = [&]() {
 #pragma unroll
         for (int q = 0; q < NLE; ++q) { const int idx = tid + q * NT; if (idx < RB * C::LW) Lrep[idx] = ((tl >> (8 * q)) & 0xFFu) * 0x01010101u; }
 #pragma unroll
-        for (int q = 0; q < NRE; ++q) { const int idx = tid + q * NT; if (idx < RB * C::RW) Ral[idx] = tr[q]; }
+        if (ASYNC_R) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        else {
+#pragma unroll
+            for (int q = 0; q < NRE; ++q) { const int idx = tid + q * NT; if (idx < RB * C::RW) Ral[idx] = tr[q]; }
+        }
     };
 
     auto phaseC = [&](int batch) {
@@ -230,8 +242,7 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
         }
         __syncthreads();
         // ---- phase B (and the tile load of the next batch) ----
-        // h >= 6: the register ring leaves no room for loads in flight across phase B (they would spill): load and store at once
-        if (batch + 1 < nbatches) { issue_tiles(rbase + RB); if (HALF >= 6) commit_tiles(); }
+        if (batch + 1 < nbatches) issue_tiles(rbase + RB);
         {
             const uint2* Hp = Hs + (kB * GT) * TWP + xlB;
 #pragma unroll
@@ -261,7 +272,7 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
                 }
             }
         }
-        if (HALF < 6 && batch + 1 < nbatches) commit_tiles();   // phase A of this batch is behind the barrier above: the tiles are free
+        if (batch + 1 < nbatches) commit_tiles();          // phase A of this batch is behind the barrier above: the tiles are free
         __syncthreads();
     }
     phaseC(nbatches - 1);
