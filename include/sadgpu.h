@@ -12,6 +12,9 @@
  *       [y0,y1) of one left/right *image.Gray pair — i.e. one or many InputChunk regions
  *       (pkg/despair/sad.go:12-15) of the same frame — and the copy loop of
  *       AssembleDisparityMap                              pkg/despair/sad.go:186-197
+ *   sadgpu_compute_region
+ *       the same worker body for ONE InputChunk (sad.go:12-15) with a region-local result buffer, exactly
+ *       OutputChunk.DisparityData (sad.go:18-21, :48-50, :91); the chunks of one frame pair share one GPU pass
  *   sadgpu_compute_sharded
  *       the row-band fan-out of OutputCamera.processDepthMap pkg/camera/output.go:172-190,
  *       with GPUs in place of goroutines
@@ -60,19 +63,20 @@ typedef struct sadgpu_tuning {
     int rows_per_batch;     /* RB: rows staged through shared memory per iteration */
     int band_rows;          /* BH: output rows per CTA band                           */
     int groups_per_chunk;   /* disparity groups (4 disparities each) per CTA chunk     */
-    int kernel_variant;     /* 0 = auto, 1 = generic (any block size), 2 = register-ring fast path (block_size <= 15),
-                               3 = warp-specialised fast path (block_size <= 9, max_disparity >= 68),
-                               4 = large-window kernel (block_size 16..31),
-                               5 = vertical-first mbarrier-pipelined kernel (block_size 10..31),
+    int kernel_variant;     /* 0 = auto, 2 = phase-alternating register-ring kernel (block_size <= 15),
+                               3 = warp-specialised kernel (block_size <= 9; the default there: chunks of 33 / 17 / 9 / 5 disparity groups
+                                   on 1 / 2 / 3 / 6 column strips per CTA, by max_disparity),
+                               4 = phase-alternating large-window kernel (block_size 16..31),
                                6 = H-ring mbarrier-pipelined kernel (block_size 10..31; the default there whenever it needs fewer passes over the
-                                   disparity range than variants 2 / 4) */
-    int reserved[4];        /* [0]: frames per launch (sadgpu_plan_describe only); [1]: developer flags (role idling, cycle counters);
+                                   disparity range than variants 2 / 4).  1 and 5 (removed kernels) are rejected. */
+    int reserved[4];        /* [0]: frames per launch (sadgpu_plan_describe only); [1]: developer flags (profile builds of the ring kernel);
                                [2] = 1: do not use TMA tile loads in the warp-specialised kernel */
 } sadgpu_tuning;
 
 int  sadgpu_device_count(void);
 
-/* devices == NULL  => devices 0..n_devices-1.  n_streams logical camera streams are created;
+/* devices == NULL  => devices 0..n_devices-1, or — when the environment variable SADGPU_DEVICES holds a comma-separated list
+ * of CUDA device ordinals — the first n_devices entries of that list (SADGPU_ERANGE if it is shorter).  n_streams logical camera streams are created;
  * stream s lives on devices[s % n_devices] and owns a CUDA stream, pinned upload/download
  * buffers and device buffers sized for max_w x max_h.  Nothing is allocated per frame. */
 int  sadgpu_create(const int *devices, int n_devices, int max_w, int max_h, int n_streams,
@@ -88,6 +92,23 @@ int  sadgpu_compute(sadgpu_ctx *ctx, int stream,
                     int w, int h, int block_size, int max_disparity, int y0, int y1,
                     uint8_t *out, int out_stride);
 
+/* ONE InputChunk of a frame pair (pkg/despair/sad.go:12-15): region [x0,x1) x [y0,y1) in image coordinates; `out` is REGION-LOCAL,
+ * row r of the region at out + r*out_stride (out_stride >= x1-x0) — with out_stride = x1-x0 exactly OutputChunk.DisparityData
+ * (sad.go:48-50, :91).  No stream argument: calls that name the same frame pair (same left / right addresses, strides, size
+ * and parameters) share ONE whole-frame GPU pass — the first call snapshots the pair into pinned memory (callers that arrive
+ * meanwhile help copying), uploads and launches; the others wait for it and slice their rectangle out of the pinned result.
+ * The reference's callers send up to 160 three-row chunks per frame (pkg/camera/output.go:172-187): this is the entry point
+ * that makes the UNCHANGED SetupConcurrentSAD worker a real drop-in.  A chunk is only served from a shared pass after the
+ * rows of its own images that influence its region ([y0-h, y1+h)) compared equal to the snapshot; otherwise the frame is
+ * recomputed from the caller's current pixels — reusing an image object for new pixels is safe.  Thread-safe; no caller
+ * pointer is retained (the addresses are remembered as keys and only ever dereferenced inside a call that passed them). */
+int  sadgpu_compute_region(sadgpu_ctx *ctx,
+                           const uint8_t *left, int left_stride, const uint8_t *right, int right_stride,
+                           int w, int h, int block_size, int max_disparity,
+                           int x0, int y0, int x1, int y1, uint8_t *out, int out_stride);
+/* Counters of the frame cache: region calls, whole-frame GPU passes they cost, chunks that met a stale snapshot. */
+int  sadgpu_region_stats(sadgpu_ctx *ctx, long long *calls, long long *frames, long long *stale);
+
 /* sadgpu_compute for a colour pair as Go decodes it: left / right are 8-bit NON-premultiplied RGBA planes,
  * 4 bytes per pixel — the Pix of an *image.NRGBA, what image/png returns for an 8-bit RGBA PNG — and the 8-bit luma is taken
  * on the device with the exact arithmetic of color.GrayModel.Convert (pkg/camera/output.go:143-147, :158-162; the same values
@@ -97,14 +118,21 @@ int  sadgpu_compute_nrgba(sadgpu_ctx *ctx, int stream,
                           const uint8_t *left_rgba, int left_stride, const uint8_t *right_rgba, int right_stride,
                           int w, int h, int block_size, int max_disparity, uint8_t *out, int out_stride);
 
-/* Asynchronous pair for per-camera pipelining.  submit copies the inputs (no caller pointer is
- * retained — cgo rule) and enqueues H2D + kernel + D2H on the stream; wait blocks until that
- * frame is done and copies rows [y0,y1) of the result to `out` (full-map addressing). */
+/* Asynchronous pair for per-camera pipelining.  submit enqueues H2D + kernel + D2H on the stream; wait blocks until that
+ * frame is done and copies rows [y0,y1) of the result to `out` (full-map addressing).
+ * Ownership of the inputs: caller memory that is NOT from sadgpu_host_alloc (a Go Pix slice) is copied into the stream's
+ * pinned staging buffer before submit returns — no caller pointer is retained (cgo rule).  Inputs that DO live in
+ * sadgpu_host_alloc memory are uploaded in place and are therefore BORROWED until the upload has run: do not overwrite them
+ * before sadgpu_wait_uploaded(ticket) (or sadgpu_wait) has returned — a camera that refills one pinned frame per capture
+ * must double-buffer or wait for the upload first.  A stream holds one frame in flight: a second submit
+ * (or sadgpu_compute) on a busy stream returns SADGPU_EBUSY; concurrent sadgpu_compute calls on one stream serialise. */
 int  sadgpu_submit(sadgpu_ctx *ctx, int stream,
                    const uint8_t *left, int left_stride, const uint8_t *right, int right_stride,
                    int w, int h, int block_size, int max_disparity, int y0, int y1,
                    uint64_t *ticket);
 int  sadgpu_wait(sadgpu_ctx *ctx, uint64_t ticket, uint8_t *out, int out_stride);
+/* Blocks until the H2D copies of the submitted frame (or batch) have run: pinned-pool inputs may be overwritten again. */
+int  sadgpu_wait_uploaded(sadgpu_ctx *ctx, uint64_t ticket);
 
 /* sadgpu_submit with the destination named up front: `out` (full-map addressing, rows [y0,y1) written) must lie in
  * memory from sadgpu_host_alloc, so the D2H copy lands in it directly and sadgpu_wait(ctx, ticket, NULL, 0) only
@@ -137,7 +165,9 @@ int  sadgpu_compute_sharded(sadgpu_ctx *ctx,
 
 /* Device-resident: dL/dR/dOut are device pointers on `device` (index into the context's
  * device list); rows [y0,y1) of dOut are written; enqueued on cuda_stream (a cudaStream_t,
- * NULL = the legacy default stream) without synchronising.  tuning may be NULL. */
+ * NULL = the legacy default stream) without synchronising.  tuning may be NULL.  Calls on different cuda_streams of one
+ * device are independent: scratch for a chunked disparity range (max_disparity > 128 at block_size <= 9, ...) is a
+ * stream-ordered allocation (cudaMallocAsync / cudaFreeAsync on cuda_stream) private to the call. */
 int  sadgpu_compute_device(sadgpu_ctx *ctx, int device,
                            const uint8_t *dL, size_t pitch_l, const uint8_t *dR, size_t pitch_r,
                            int w, int h, int block_size, int max_disparity, int y0, int y1,
@@ -169,7 +199,7 @@ void *sadgpu_host_alloc(sadgpu_ctx *ctx, size_t bytes);
 void  sadgpu_host_free(sadgpu_ctx *ctx, void *p);
 
 /* Introspection used by bench.py / tests. */
-int  sadgpu_debug_read(sadgpu_ctx *ctx, int device, uint32_t *host, int n_words);   /* developer: per-role cycle counters (tuning.reserved[1] & 4) */
+int  sadgpu_debug_read(sadgpu_ctx *ctx, int device, uint32_t *host, int n_words);   /* developer: per-role cycle counters (library built with -DRING_PROFILE, tuning.reserved[1] & 4) */
 int  sadgpu_last_launch_count(sadgpu_ctx *ctx);    /* kernels launched by the last compute call */
 int  sadgpu_plan_describe(int w, int h, int block_size, int max_disparity, int y0, int y1,
                           const sadgpu_tuning *tuning, char *buf, size_t buflen);

@@ -10,24 +10,9 @@
 //   * several frames are processed by one launch (blockIdx.z = frame x chunk) so that the grid
 //     is many waves deep and the single-wave tail disappears.
 #pragma once
-#include <cstdint>
-#include <cuda.h>
-#include <cuda_runtime.h>
+#include "sad_common.cuh"
 
 namespace sadgpu {
-
-struct FastArgs {
-    CUtensorMap tmapL, tmapR;                // TMA descriptors (warp-specialised kernel, use_tma != 0); 64-byte aligned, first members
-    const uint8_t* L; const uint8_t* R; uint8_t* out; uint32_t* gkey;
-    long long frameL, frameR, frameOut;      // byte strides between frames of a batch
-    int pitchL, pitchR, pitchOut;
-    int W, H, y0, y1;
-    int D, NG, NC, BH;
-    int aligned;                             // R rows may be fetched with aligned 32-bit loads
-    int use_tma;                             // tile loads by cp.async.bulk.tensor (needs 16-byte aligned base / pitch / frame stride)
-    int debug_skip;                          // developer experiments: 1 = walkers idle, 2 = consumers idle (results wrong)
-    unsigned k65536;                         // = 65536, passed at run time so that v*65536+idx stays an IMAD (FMA pipe)
-};
 
 template <int HALF> struct FastTraits {
     static constexpr int WIN = 2 * HALF + 1;
@@ -37,8 +22,8 @@ template <int HALF> struct FastTraits {
     static constexpr int LW = (NSTEP + 3) & ~3;                     // words per replicated-L row
     static constexpr int RB = WIN >= 7 ? WIN : WIN * ((8 + WIN - 1) / WIN);   // rows per batch (multiple of WIN)
     static constexpr bool BIAS = WIN * WIN * 255 + 32768 < 65536;   // h <= 5
-    static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;         // byte phase of the R walk in its aligned word
-    static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;     // aligned R words one walk touches
+    static constexpr int OFF = walk_off(HALF);                      // byte phase of the R walk in its aligned word
+    static constexpr int NWALKW = walk_words(HALF, NSTEP);          // aligned R words one walk touches
 };
 
 template <int HALF, int NGC> struct FastCfg : FastTraits<HALF> {
@@ -60,40 +45,6 @@ template <int HALF, int NGC> struct FastCfg : FastTraits<HALF> {
     static constexpr int OFF_LUT = OFF_PK + PK_BYTES;
     static constexpr int SMEM = OFF_LUT + LUT_BYTES;
 };
-
-// Keys (sum << 16 | index).  Low lane: one IMAD (FMA pipe) with the multiplier 65536 held in a register and the
-// index as immediate addend; high lane: one LOP3 (ALU pipe), (v & mask) | index, mask held in a register.
-// Both constants are made opaque so that ptxas keeps them in registers instead of re-materialising them.
-__device__ __forceinline__ uint32_t opaque(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
-__device__ __forceinline__ uint32_t key_lo(uint32_t v, uint32_t k65536, uint32_t idx) { return v * k65536 + idx; }
-__device__ __forceinline__ uint32_t key_hi(uint32_t v, uint32_t maskhi, uint32_t idx) { return (v & maskhi) | idx; }
-
-// ---- phase A: one (row, group) walk, fully unrolled --------------------------------------
-template <int HALF, bool EDGE>
-__device__ __forceinline__ void fast_walk(const uint32_t* __restrict__ Lr, const uint32_t* __restrict__ Rr,
-                                          uint2* __restrict__ Hout, int nvalid)
-{
-    using T = FastTraits<HALF>;
-    uint32_t e[T::NSTEP], o[T::NSTEP];
-    uint32_t hE = 0, hO = 0, w0 = 0, w1 = 0;
-    uint4 lv = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < T::NSTEP; ++i) {
-        if ((i & 3) == 0) lv = *reinterpret_cast<const uint4*>(Lr + i);
-        const int bi = i + T::OFF;
-        if (i == 0) { w0 = Rr[bi >> 2]; w1 = Rr[(bi >> 2) + 1]; }
-        else if ((bi & 3) == 0) { w0 = w1; w1 = Rr[(bi >> 2) + 1]; }
-        const uint32_t lw = (i & 3) == 0 ? lv.x : (i & 3) == 1 ? lv.y : (i & 3) == 2 ? lv.z : lv.w;
-        const uint32_t rw = (bi & 3) == 0 ? w0 : __funnelshift_r(w0, w1, 8 * (bi & 3));
-        uint32_t ad = __vabsdiffu4(lw, rw);
-        if (EDGE) ad = (i < nvalid) ? ad : 0u;                  // columns x' >= W contribute nothing
-        e[i] = __byte_perm(ad, 0u, 0x4240);                     // (d=4g+3 | d=4g+1 << 16)
-        o[i] = __byte_perm(ad, 0u, 0x4341);                     // (d=4g+2 | d=4g   << 16)
-        if (i >= T::WIN) { hE = hE + e[i] - e[i - T::WIN]; hO = hO + o[i] - o[i - T::WIN]; }
-        else             { hE += e[i]; hO += o[i]; }
-        if (i >= 2 * HALF) Hout[i - 2 * HALF] = make_uint2(hE, hO);
-    }
-}
 
 template <int HALF, int NGC>
 __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(const FastArgs a)
@@ -237,8 +188,8 @@ __global__ void __launch_bounds__(FastCfg<HALF, NGC>::NT, 1) sad_fast_kernel(con
             const uint32_t* Lr = Lrep + rb * C::LW;
             const uint32_t* Rr = Ral + rb * C::RW + (NGC - 1 - gl);
             uint2* Hout = Hs + (rb * NGP + gl) * TWP;
-            if (nvalid >= C::NSTEP) fast_walk<HALF, false>(Lr, Rr, Hout, nvalid);
-            else                    fast_walk<HALF, true>(Lr, Rr, Hout, nvalid);
+            if (nvalid >= C::NSTEP) sad_walk<HALF, TW, false>(Lr, Rr, Hout, nvalid);
+            else                    sad_walk<HALF, TW, true>(Lr, Rr, Hout, nvalid);
         }
         __syncthreads();
         // ---- phase B (and the tile load of the next batch) ----

@@ -148,34 +148,6 @@ __device__ __forceinline__ void ring_wait_(uint32_t bar, uint32_t parity)
 #define RING_PROF_END(dbg) do {} while (0)
 #endif
 
-// One walk of NOUT outputs (NOUT + 2h steps, fully unrolled): Lr / Rr / Hout point at the first step's operands.
-template <int HALF, int NOUT, bool EDGE>
-__device__ __forceinline__ void ring_walk(const uint32_t* __restrict__ Lr, const uint32_t* __restrict__ Rr,
-                                          uint2* __restrict__ Hout, int nvalid, bool store)
-{
-    using T = RingCfg<HALF>;
-    constexpr int NS = NOUT + 2 * HALF;
-    uint32_t e[NS], o[NS];
-    uint32_t hE = 0, hO = 0, w0 = 0, w1 = 0;
-    uint4 lv = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        if ((i & 3) == 0) lv = *reinterpret_cast<const uint4*>(Lr + i);
-        const int bi = i + T::OFF;
-        if (i == 0) { w0 = Rr[bi >> 2]; w1 = Rr[(bi >> 2) + 1]; }
-        else if ((bi & 3) == 0) { w0 = w1; w1 = Rr[(bi >> 2) + 1]; }
-        const uint32_t lw = (i & 3) == 0 ? lv.x : (i & 3) == 1 ? lv.y : (i & 3) == 2 ? lv.z : lv.w;
-        const uint32_t rw = (bi & 3) == 0 ? w0 : __funnelshift_r(w0, w1, 8 * (bi & 3));
-        uint32_t ad = __vabsdiffu4(lw, rw);
-        if (EDGE) ad = (i < nvalid) ? ad : 0u;                  // columns x >= W contribute nothing
-        e[i] = __byte_perm(ad, 0u, 0x4240);                     // (d=4g+3 | d=4g+1 << 16)
-        o[i] = __byte_perm(ad, 0u, 0x4341);                     // (d=4g+2 | d=4g   << 16)
-        if (i >= T::WIN) { hE = hE + e[i] - e[i - T::WIN]; hO = hO + o[i] - o[i - T::WIN]; }
-        else             { hE += e[i]; hO += o[i]; }
-        if (i >= 2 * HALF && store) Hout[i - 2 * HALF] = make_uint2(hE, hO);
-    }
-}
-
 template <int HALF>
 __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __grid_constant__ FastArgs a)
 {
@@ -248,8 +220,8 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                 if (r < nin) {
                     RING_WAIT(tfull + 8 * ts, (uint32_t)(r / TR) & 1u, 0);
                     if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
-                    if (nvalid >= C::NSTEP) ring_walk<HALF, HW, false>(Lr, Rr, Hout, nvalid - HW * wh, true);
-                    else                    ring_walk<HALF, HW, true>(Lr, Rr, Hout, nvalid - HW * wh, true);
+                    if (nvalid >= C::NSTEP) sad_walk<HALF, HW, false>(Lr, Rr, Hout, nvalid - HW * wh, true);
+                    else                    sad_walk<HALF, HW, true>(Lr, Rr, Hout, nvalid - HW * wh, true);
                     __syncwarp();
                     if (lane == 0) ring_arrive(tempty + 8 * ts);
                 }
@@ -259,8 +231,8 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                 if (C::ROWREL) { if (act && r >= NRH) RING_WAIT(hempty + 8 * (r % NRH), (uint32_t)(r / NRH - 1) & 1u, 1); }
                 else if (bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
                 __syncwarp();
-                if (nvalid >= C::NSTEP) ring_walk<HALF, HW, false>(Lr, Rr, Hout, nvalid - HW * wh, act);
-                else                    ring_walk<HALF, HW, true>(Lr, Rr, Hout, nvalid - HW * wh, act);
+                if (nvalid >= C::NSTEP) sad_walk<HALF, HW, false>(Lr, Rr, Hout, nvalid - HW * wh, act);
+                else                    sad_walk<HALF, HW, true>(Lr, Rr, Hout, nvalid - HW * wh, act);
                 __syncwarp();
                 if (act && (lane & 15) == 0) ring_arrive(tempty + 8 * ts);
             }
@@ -286,8 +258,8 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                 const uint32_t* Lr = Lrep + ts * LW + C::SEGW * s;
                 const uint32_t* Rr = Ral + ts * RW + (C::SEGW / 4) * s;
                 uint2* Hout = Hs + (bs * NWK + ((C::TPASS == 1 || j < NWK) ? j : 0)) * HROW + (NGC - 1) * TWP + C::SEGW * s;
-                if (nvalid >= C::NSTEP) ring_walk<HALF, C::SEGW, false>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
-                else                    ring_walk<HALF, C::SEGW, true>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
+                if (nvalid >= C::NSTEP) sad_walk<HALF, C::SEGW, false>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
+                else                    sad_walk<HALF, C::SEGW, true>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
                 __syncwarp();
                 if (act && s == 0) ring_arrive(tempty + 8 * ts);
             }

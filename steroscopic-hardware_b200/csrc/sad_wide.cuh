@@ -45,33 +45,6 @@ template <int HALF> struct WideCfg {
     static constexpr uint32_t BIAS = 1u << 22;                      // > any window sum (245 055); (BIAS + sum) * 512 < 2^32
 };
 
-// One segment of a (row, group) walk: SEGW outputs, SEGW+2h steps, fully unrolled.  Lr / Rr point at the segment start.
-template <int HALF, bool EDGE>
-__device__ __forceinline__ void wide_walk(const uint32_t* __restrict__ Lr, const uint32_t* __restrict__ Rr,
-                                          uint2* __restrict__ Hout, int nvalid)
-{
-    using T = WideCfg<HALF>;
-    uint32_t e[T::SSTEP], o[T::SSTEP];
-    uint32_t hE = 0, hO = 0, w0 = 0, w1 = 0;
-    uint4 lv = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < T::SSTEP; ++i) {
-        if ((i & 3) == 0) lv = *reinterpret_cast<const uint4*>(Lr + i);
-        const int bi = i + T::OFF;
-        if (i == 0) { w0 = Rr[bi >> 2]; w1 = Rr[(bi >> 2) + 1]; }
-        else if ((bi & 3) == 0) { w0 = w1; w1 = Rr[(bi >> 2) + 1]; }
-        const uint32_t lw = (i & 3) == 0 ? lv.x : (i & 3) == 1 ? lv.y : (i & 3) == 2 ? lv.z : lv.w;
-        const uint32_t rw = (bi & 3) == 0 ? w0 : __funnelshift_r(w0, w1, 8 * (bi & 3));
-        uint32_t ad = __vabsdiffu4(lw, rw);
-        if (EDGE) ad = (i < nvalid) ? ad : 0u;
-        e[i] = __byte_perm(ad, 0u, 0x4240);
-        o[i] = __byte_perm(ad, 0u, 0x4341);
-        if (i >= T::WIN) { hE = hE + e[i] - e[i - T::WIN]; hO = hO + o[i] - o[i - T::WIN]; }
-        else             { hE += e[i]; hO += o[i]; }
-        if (i >= 2 * HALF) Hout[i - 2 * HALF] = make_uint2(hE, hO);
-    }
-}
-
 template <int HALF>
 __global__ void __launch_bounds__(WideCfg<HALF>::NT, 1) sad_wide_kernel(const FastArgs a)
 {
@@ -189,8 +162,8 @@ __global__ void __launch_bounds__(WideCfg<HALF>::NT, 1) sad_wide_kernel(const Fa
             const uint32_t* Rr = Ral + rb * C::RW + (NGC - 1 - gl) + seg * (C::SEGW / 4);
             uint2* Hout = Hs + slot * HROW + gl * TWP + seg * C::SEGW;
             const int nv = nvalid - seg * C::SEGW;
-            if (nv >= C::SSTEP) wide_walk<HALF, false>(Lr, Rr, Hout, nv);
-            else                wide_walk<HALF, true>(Lr, Rr, Hout, nv);
+            if (nv >= C::SSTEP) sad_walk<HALF, C::SEGW, false>(Lr, Rr, Hout, nv);
+            else                sad_walk<HALF, C::SEGW, true>(Lr, Rr, Hout, nv);
         }
         __syncthreads();
         // ---- phase B (and the tile load of the next batch) ----

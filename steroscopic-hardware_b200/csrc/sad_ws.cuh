@@ -1,53 +1,100 @@
-// sad_ws.cuh — warp-specialised, double-buffered variant of the fast path (block_size <= 9, chunks of
-// 33 disparity groups = 132 disparity slots, i.e. max_disparity 65..128 in one chunk, up to 256 in two).
+// sad_ws.cuh — warp-specialised, double-buffered kernel for block_size <= 9 (h <= 4), every max_disparity.
 //
-// Same arithmetic as sad_fast.cuh; the difference is scheduling.  A CTA owns a 32-column strip and has
-// 24 warps with FIXED roles (no phase alternation, one __syncthreads per 9-row batch), registers rebalanced
-// between the roles with setmaxnreg:
-//   warps 0..8   walkers: warp w walks row w of the batch for 32 disparity groups (lanes = groups),
-//                horizontal running window sums -> H[buf][row][group][column] in shared memory;
-//   warp  9      walks the 33rd group (the single candidate d = 128 when D = 128), one lane per row;
-//                each walker also prefetches its row of the batch after next (three tile buffers);
-//   warp  10     finisher: min over the 11 partial keys of a pixel, d*255/D LUT, store;
-//   warps 12..22 consumers: warp 12+k owns groups 3k..3k+2 for 32 columns (lanes = columns): vertical
-//                running sums with the previous 2h+1 rows in a register ring, key-min argmin, partial
-//                best -> pk; then the cross-warp min + LUT + store of the batch before.
-// Producers work on batch i while consumers work on batch i-1 (H and tiles are double-buffered).
+// Arithmetic: sad_common.cuh.  Scheduling: a CTA owns NS adjacent 32-column strips of one row band and has 24 warps
+// with FIXED roles (no phase alternation, one __syncthreads per 10-row batch), registers rebalanced between the roles
+// with setmaxnreg:
+//   warps 0..9   walkers: warp w walks row w of the batch; its 32 lanes are (strip, disparity group) pairs:
+//                horizontal running window sums -> H[buf][row][strip][group][column] in shared memory;
+//   warp 10      tail walker (modes with a tail group: the last group of the chunk, one lane per (row, strip));
+//   warp 11      TMA loader (cp.async.bulk.tensor.3d + mbarrier, hardware zero fill outside the image; it also
+//                replicates the left pixels);
+//   warps 12..23 consumers: a warp owns 2 or 3 groups of one strip for 32 columns (lanes = columns): vertical running
+//                sums with the previous rows in a REGISTER ring (shared memory carries every H value once), key-min
+//                argmin; the consumers of a strip meet in ONE key per pixel through a shared-memory atomicMin.  Each
+//                consumer warp also finishes a twelfth of the pixel rows of the batch before: key -> d*255/D LUT -> store.
+// Producers work on batch i while consumers work on batch i-1 (H is double-buffered, tiles are requested three
+// batches ahead).
+//
+// Two things set the speed of this kernel once the arithmetic is fixed (profiles/r02_ws_*):
+//   * the ring is 10 rows long, one more than the largest window (9): the slot a row is loaded into was read for the
+//     last time one row earlier, so the load lands in it directly and no register is ever moved (a 9-row ring of a
+//     9-row window costs two moves per group and row: 7 % of all instructions in round 1);
+//   * an SM sub-partition issues one instruction per clock for ALL its warps (warp w lives on sub-partition w % 4), so
+//     the batch time is the instruction count of the most loaded sub-partition.  The roles above put 3 + 3 + (2 + tail)
+//     + (2 + loader/finisher) producer warps on the four sub-partitions and the consumer table below deals the groups
+//     so that every sub-partition ends up with about the same number of instructions per batch.
+//
+// MODE = how the walker lanes are spent, i.e. which disparity ranges fill the machine:
+//   0: 1 strip  x 32 groups + tail  = chunks of 33 groups (132 disparity slots): max_disparity 65..128, 256 in two chunks
+//   1: 2 strips x 16 groups + tail  = 17 groups: max_disparity 33..64 (the reference's default range, params.go:13-18)
+//   2: 3 strips x  9 groups         =  9 groups: max_disparity 17..32
+//   3: 6 strips x  5 groups         =  5 groups: max_disparity <= 16
 #pragma once
-#include <cstdint>
-#include <cuda_runtime.h>
-#include "sad_fast.cuh"
+#include "sad_common.cuh"
 
 namespace sadgpu {
 
-template <int HALF> struct WsCfg {
+// Consumer warp k (= warp - 12, sub-partition k % 4) -> (strip, first group, number of groups).
+struct WsShare { int strip, first, ng; };
+__host__ __device__ constexpr WsShare ws_share(int mode, int k)
+{
+    if (mode == 0) {                    // 33 groups: sub-partitions 0..2 (three walker / tail warps each) take 8, sub-partition 3 takes 9
+        const int first = k <= 8 ? 3 * k : 24 + 2 * (k - 8);               // 3 3 3 3  3 3 3 3  2 2 2 3
+        return WsShare{0, first, (k >= 8 && k <= 10) ? 2 : 3};
+    }
+    if (mode == 1) {                    // 2 x 17 groups: six warps per strip, 3 3 3 3 3 2
+        const int s = k / 6, i = k % 6;
+        return WsShare{s, 3 * i, i == 5 ? 2 : 3};
+    }
+    if (mode == 2) {                    // 3 x 9 groups: four warps per strip, the 3-group warp rotates over the sub-partitions
+        const int s = k / 4, i = k % 4;
+        return WsShare{s, 2 * i + (i > s ? 1 : 0), i == s ? 3 : 2};
+    }
+    // 6 x 5 groups: two warps per strip, 3 + 2 or 2 + 3
+    const int s = k / 2, i = k % 2;
+    const int n0 = (s == 0 || s == 3 || s == 4) ? 3 : 2;
+    return WsShare{s, i == 0 ? 0 : n0, i == 0 ? n0 : 5 - n0};
+}
+
+template <int HALF, int MODE> struct WsCfg {
+    static_assert(HALF >= 0 && HALF <= 4 && MODE >= 0 && MODE <= 3, "warp-specialised kernel: block_size <= 9");
     static constexpr int WIN = 2 * HALF + 1;
-    static constexpr int TW = 32, TWP = 33;
-    static constexpr int NSTEP = TW + 2 * HALF;
-    static constexpr int LW = (NSTEP + 3) & ~3;
-    static constexpr int RB = 9;                       // rows per batch = row-walker warps = ring length
-    static constexpr int NGC = 33, GT = 3, K = 11;     // groups per chunk, groups per consumer thread, consumer warps
-    // warp roles (6 warpgroups of 4 warps): producers = warps 0..11, consumers = warps 12..23
-    static constexpr int W_TAIL = RB;                  // warp 9: 33rd group, one lane per row
-    static constexpr int W_FIN = 10;                   // warp 10: cross-warp min + LUT + store (warp 11 idles)
+    static constexpr int NS = MODE == 0 ? 1 : MODE == 1 ? 2 : MODE == 2 ? 3 : 6;       // strips per CTA
+    static constexpr int NGL = MODE == 0 ? 32 : MODE == 1 ? 16 : MODE == 2 ? 9 : 5;    // groups walked by the row warps
+    static constexpr bool TAIL = MODE <= 1;                                            // one more group, walked by the tail warp
+    static constexpr int NGC = NGL + (TAIL ? 1 : 0);                                   // groups per chunk
+    static constexpr int TW = 32, TWP = 33, CW = NS * TW;                              // strip / padded strip / CTA width
+    static constexpr int NSTEP = TW + 2 * HALF;                                        // steps of one strip walk
+    static constexpr int LW = (CW + 2 * HALF + 3) & ~3;                                // replicated left pixels per tile row
+    static constexpr int RB = 10;                      // rows per batch = row-walker warps = length of the register ring (> the window)
+    static constexpr int K = 12;                       // consumer warps
+    static constexpr int NSLOT = NS * NGC;             // group slots of an H row
+    // warp roles (6 warpgroups of 4 warps): producer class = warps 0..11, consumer class = warps 12..23
+    static constexpr int W_AUX = RB;                   // warp 10: tail walker (idle in the modes without a tail group)
+    static constexpr int W_LOAD = 11;                  // tile loader
+    static constexpr int W_CONS = 12;
+    // finishing (key -> LUT -> store) of the batch before the one consumed.  One strip: the loader warp does it (its sub-partition
+    // has the fewest instructions; measured 67 vs 73 us at D = 128).  Several strips: 20..60 rows per batch are too long a chain
+    // for one warp, so item (strip, row) t belongs to consumer warp t % K (measured 46.6 -> 40.8 us at D = 64, 37.7 -> 19.3 at D = 16).
+    static constexpr bool FIN_CONS = NS > 1;
+    static constexpr int NFI = (NS * RB + K - 1) / K;
     static constexpr int NTILE = 4;                    // tile buffers: tiles are requested three batches ahead, completed two ahead
-    static constexpr int W_CONS = 12;                  // warps 12..22: consumer k = warp-12 (warp 23 idles)
     static constexpr int NT = 768;
     static constexpr int REGS_LAUNCH = 80, REGS_PROD = 56, REGS_CONS = 104;
-    static constexpr int REGS_PROD_TMA = 40, REGS_CONS_TMA = 120;           // with TMA the walkers carry no prefetch state   // setmaxnreg moves registers inside the CTA's launch allocation
-    static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
-    static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;
-    static constexpr int RW = NGC - 1 + NWALKW;
-    static constexpr int H_BYTES = ((RB * NGC * TWP * 8 + 15) / 16) * 16;      // one buffer
+    static constexpr int REGS_PROD_TMA = 40, REGS_CONS_TMA = 120;           // with TMA the walkers carry no prefetch state; setmaxnreg moves registers inside the CTA's launch allocation
+    static constexpr int OFF = walk_off(HALF);
+    static constexpr int NWALKW = walk_words(HALF, NSTEP);
+    static constexpr int RW = NGC - 1 + (TW / 4) * (NS - 1) + NWALKW;       // aligned right words per tile row
+    static constexpr int H_BYTES = ((RB * NSLOT * TWP * 8 + 15) / 16) * 16;  // one buffer
     static constexpr int L_BYTES = RB * LW * 4;
     // TMA needs the innermost start coordinate on a 16-byte boundary: the right tile starts up to 12 bytes early (RWT words
     // per row), the raw left tile LSH bytes early (x0 is a multiple of 32, so LSH only depends on h).
     static constexpr int RWT = ((RW * 4 + 12 + 15) / 16) * 4;
     static constexpr int R_BYTES = ((RB * RWT * 4 + 127) / 128) * 128;        // 128-byte multiple: each buffer is a TMA destination
     static constexpr int LSH = (16 - HALF % 16) % 16;
-    static constexpr int LBOX = ((LSH + NSTEP + 15) / 16) * 16;               // TMA box width of the raw left tile (bytes)
+    static constexpr int LBOX = ((LSH + LW + 15) / 16) * 16;                  // TMA box width of the raw left tile (bytes)
     static constexpr int LRAW_BYTES = ((RB * LBOX + 127) / 128) * 128;
-    static constexpr int PK_BYTES = RB * K * TW * 4;
+    static constexpr int PK_BYTES = RB * NS * TW * 4;                         // ONE key per pixel and row
     static constexpr int OFF_R = ((2 * H_BYTES + 127) / 128) * 128;            // TMA destinations first (128-byte aligned)
     static constexpr int OFF_LRAW = OFF_R + NTILE * R_BYTES;
     static constexpr int OFF_L = OFF_LRAW + NTILE * LRAW_BYTES;
@@ -55,52 +102,57 @@ template <int HALF> struct WsCfg {
     static constexpr int OFF_LUT = OFF_PK + 2 * PK_BYTES;
     static constexpr int OFF_MBAR = OFF_LUT + 1040;
     static constexpr int SMEM = OFF_MBAR + 64;
-    static_assert(WIN <= RB, "register ring shorter than the window");
+    static_assert(WIN < RB, "the ring must be longer than the window");
     static_assert(NT * REGS_LAUNCH <= 65536 && 384 * REGS_PROD + 384 * REGS_CONS <= NT * REGS_LAUNCH, "register budget");
-    static_assert(GT * K == NGC && W_CONS + K <= 24, "warp roles");
+    static_assert(NS * NGL <= 32 && (!TAIL || RB * NS <= 32), "walker lanes");
+    static_assert(RWT * 4 <= 256 && LBOX <= 256 && RB <= 256, "TMA box");
+    static_assert(SMEM <= 232448, "shared memory");
 };
 
-// One (row, group) walk: TW outputs, NSTEP steps, fully unrolled (see fast_walk in sad_fast.cuh).
-template <int HALF, bool EDGE>
-__device__ __forceinline__ void ws_walk(const uint32_t* __restrict__ Lr, const uint32_t* __restrict__ Rr,
-                                        uint2* __restrict__ Hout, int nvalid)
-{
-    using T = WsCfg<HALF>;
-    uint32_t e[T::NSTEP], o[T::NSTEP];
-    uint32_t hE = 0, hO = 0, w0 = 0, w1 = 0;
-    uint4 lv = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < T::NSTEP; ++i) {
-        if ((i & 3) == 0) lv = *reinterpret_cast<const uint4*>(Lr + i);
-        const int bi = i + T::OFF;
-        if (i == 0) { w0 = Rr[bi >> 2]; w1 = Rr[(bi >> 2) + 1]; }
-        else if ((bi & 3) == 0) { w0 = w1; w1 = Rr[(bi >> 2) + 1]; }
-        const uint32_t lw = (i & 3) == 0 ? lv.x : (i & 3) == 1 ? lv.y : (i & 3) == 2 ? lv.z : lv.w;
-        const uint32_t rw = (bi & 3) == 0 ? w0 : __funnelshift_r(w0, w1, 8 * (bi & 3));
-        uint32_t ad = __vabsdiffu4(lw, rw);
-        if (EDGE) ad = (i < nvalid) ? ad : 0u;
-        e[i] = __byte_perm(ad, 0u, 0x4240);
-        o[i] = __byte_perm(ad, 0u, 0x4341);
-        if (i >= T::WIN) { hE = hE + e[i] - e[i - T::WIN]; hO = hO + o[i] - o[i - T::WIN]; }
-        else             { hE += e[i]; hO += o[i]; }
-        if (i >= 2 * HALF) Hout[i - 2 * HALF] = make_uint2(hE, hO);
-    }
-}
-
-// Consumer warp: NGB groups (20 or 12 disparities) x 32 columns; one barrier per batch.
-template <int HALF, int NGB>
+// Consumer warp: NG groups (first group gf of strip s) x 32 columns; one barrier per batch.
+template <int HALF, int MODE, int NG>
 __device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __restrict__ Hs, uint32_t* __restrict__ pk,
-                                           int kB, int lane, int x0, int g0, int r0, int nb)
+                                           const uint8_t* __restrict__ lut, int kB, int s, int gf, int lane, int frame,
+                                           int x0, int g0, int r0, int yb1, int nb)
 {
-    using C = WsCfg<HALF>;
-    constexpr int WIN = C::WIN, TW = C::TW, TWP = C::TWP, RB = C::RB, GT = C::GT, K = C::K, NGC = C::NGC;
-    constexpr int HBUF = C::H_BYTES / 8, PKBUF = RB * K * TW;
-    const int xB = x0 + lane;
-    uint32_t VE[NGB], VO[NGB], ringE[RB][NGB], ringO[RB][NGB];
+    using C = WsCfg<HALF, MODE>;
+    constexpr int WIN = C::WIN, TW = C::TW, TWP = C::TWP, RB = C::RB, NS = C::NS;
+    constexpr int HBUF = C::H_BYTES / 8, HROW = C::NSLOT * TWP, PKBUF = RB * C::NS * TW;
+    const int xB = x0 + s * TW + lane;
+    // finishing share of this warp: items t = kB, kB + K, ... (strip t / RB, row t % RB) of the batch before the one consumed
+    uint8_t* __restrict__ Og = a.out + (long long)frame * a.frameOut;
+    int fs[C::NFI], frb[C::NFI];
+    bool fx[C::NFI], fz[C::NFI];
 #pragma unroll
-    for (int j = 0; j < NGB; ++j) {
-        const int dbase = 4 * (g0 + kB * GT + j);
-        const int dmax = min(a.D, xB - HALF);
+    for (int i = 0; i < (C::FIN_CONS ? C::NFI : 0); ++i) {
+        const int t = kB + C::K * i;
+        fs[i] = t / RB; frb[i] = t - fs[i] * RB;
+        const int x = x0 + fs[i] * TW + lane;
+        fx[i] = t < NS * RB && x < a.W;
+        fz[i] = x < HALF;                                      // X < h: both windows clamp, d = 0 wins (sad.go:212-218)
+    }
+    auto finish = [&](int batch) {
+        uint32_t* pkb = pk + (batch & 1) * PKBUF + lane;
+        const int row0 = r0 + batch * RB - HALF;               // image row of item row 0
+        const int rb_lo = 2 * HALF - batch * RB, rb_hi = yb1 - row0;   // output rows of this batch: rb in [rb_lo, rb_hi)
+#pragma unroll
+        for (int i = 0; i < C::NFI; ++i) {
+            if (kB + C::K * i >= NS * RB) continue;            // warp-uniform
+            uint32_t* q = pkb + (frb[i] * NS + fs[i]) * TW;
+            uint32_t best = *q;
+            *q = 0xFFFFFFFFu;                                  // re-arm for the batch after next
+            if (fz[i]) best = 0;
+            const bool ok = fx[i] && frb[i] >= rb_lo && frb[i] < rb_hi;
+            const int x = x0 + fs[i] * TW + lane, y = row0 + frb[i];
+            if (a.NC == 1) { const uint8_t v = lut[best & 0xFFFFu]; if (ok) Og[(long long)y * a.pitchOut + x] = v; }
+            else if (ok) atomicMin(a.gkey + ((long long)frame * a.H + y) * a.W + x, ((best >> 16) << 9) | (best & 511u));
+        }
+    };
+    uint32_t VE[NG], VO[NG], ringE[RB][NG], ringO[RB][NG];
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+        const int dbase = 4 * (g0 + gf + j);
+        const int dmax = min(a.D, xB - HALF);                 // largest evaluated disparity of this column (sad.go:64-67, :212-218)
         const uint32_t iE = (dbase + 3 > dmax ? 0x0000FFFFu : 0u) | (dbase + 1 > dmax ? 0xFFFF0000u : 0u);
         const uint32_t iO = (dbase + 2 > dmax ? 0x0000FFFFu : 0u) | (dbase + 0 > dmax ? 0xFFFF0000u : 0u);
         VE[j] = iE & 0x80008000u;                             // bias: never-evaluated candidates lose
@@ -108,26 +160,23 @@ __device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __res
 #pragma unroll
         for (int r = 0; r < RB; ++r) { ringE[r][j] = 0; ringO[r][j] = 0; }
     }
-    const uint32_t keybase = 4u * (uint32_t)(g0 + kB * GT);
+    const uint32_t keybase = 4u * (uint32_t)(g0 + gf);
     const uint32_t k16 = opaque(a.k65536), mhi = opaque(a.k65536 * 0xFFFFu);
-    long long tw = 0, tb = 0, cprev = 0;
-    // unrolled by two so that the ring registers can alternate roles across iterations (the value loaded for row rb is
-    // the "old" value of the next batch): without it every ring update costs a register move
-#pragma unroll 2
+    const uint2* Hbase = Hs + (s * C::NGC + gf) * TWP + lane;
+    uint32_t* pkbase = pk + s * TW + lane;
     for (int it = 0; it < nb + 2; ++it) {
-        if (a.debug_skip & 4) { const volatile uint32_t* vq = pk; tw += (long long)(vq[0] & 0u); }       // forces the deferred barrier wait to complete
-        const long long c0 = clock64();
-        if ((a.debug_skip & 4) && it > 0) tb += c0 - cprev;
-        if (it >= 1 && it <= nb && (a.debug_skip & 3) != 2) {
+        if (C::FIN_CONS && it >= 2) finish(it - 2);
+        if (it >= 1 && it <= nb) {
             const int batch = it - 1;
-            const uint2* Hp = Hs + (batch & 1) * HBUF + (kB * GT) * TWP + lane;
-            uint32_t* pkb = pk + (batch & 1) * PKBUF + kB * TW + lane;
+            const uint2* Hp = Hbase + (batch & 1) * HBUF;
+            uint32_t* pkb = pkbase + (batch & 1) * PKBUF;
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) {
                 uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
-                for (int j = 0; j < NGB; ++j) {
-                    const uint2 n = Hp[(rb * NGC + j) * TWP];
+                for (int j = 0; j < NG; ++j) {
+                    // the slot of row rb was read for the last time one row ago (WIN < RB): the load lands in it directly
+                    const uint2 n = Hp[rb * HROW + j * TWP];
                     VE[j] = VE[j] + n.x - ringE[(rb + RB - WIN) % RB][j];
                     VO[j] = VO[j] + n.y - ringO[(rb + RB - WIN) % RB][j];
                     ringE[rb][j] = n.x; ringO[rb][j] = n.y;
@@ -138,162 +187,165 @@ __device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __res
                     best = min(best, min(kEl, kEh));
                     best = min(best, min(kOl, kOh));
                 }
-                pkb[rb * K * TW] = best + keybase;            // rows that are not output rows are filtered by the finisher
+                atomicMin(pkb + rb * C::NS * TW, best + keybase);    // rows that are not output rows are filtered by the finisher
             }
         }
-        const long long c1 = clock64();
         __syncthreads();
-        if (a.debug_skip & 4) { tw += c1 - c0; cprev = c1; }
-    }
-    if ((a.debug_skip & 4) && lane == 0 && blockIdx.x == 7 && blockIdx.y == 0 && blockIdx.z == 0) {
-        const int warp = kB + C::W_CONS;
-        a.gkey[warp * 4 + 0] = (uint32_t)tw; a.gkey[warp * 4 + 1] = 0; a.gkey[warp * 4 + 2] = (uint32_t)tb; a.gkey[warp * 4 + 3] = nb;
     }
 }
 
-template <int HALF, bool TMA>
-__global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid_constant__ FastArgs a)
+template <int HALF, int MODE, bool TMA>
+__global__ void __launch_bounds__(WsCfg<HALF, MODE>::NT, 1) sad_ws_kernel(const __grid_constant__ FastArgs a)
 {
-    using C = WsCfg<HALF>;
-    constexpr int WIN = C::WIN, TW = C::TW, TWP = C::TWP, RB = C::RB, GT = C::GT, K = C::K, NGC = C::NGC;
+    using C = WsCfg<HALF, MODE>;
+    constexpr int TW = C::TW, TWP = C::TWP, RB = C::RB, NGC = C::NGC, NS = C::NS, NGL = C::NGL;
     extern __shared__ __align__(128) unsigned char smem[];
-    uint2* Hs = reinterpret_cast<uint2*>(smem);                                   // [2][RB][NGC][TWP]
-    uint32_t* Lrep = reinterpret_cast<uint32_t*>(smem + C::OFF_L);               // [2][RB][LW]
-    uint32_t* Ral = reinterpret_cast<uint32_t*>(smem + C::OFF_R);                // [2][RB][RW]
-    uint32_t* pk = reinterpret_cast<uint32_t*>(smem + C::OFF_PK);                // [2][RB][K][TW]
+    uint2* Hs = reinterpret_cast<uint2*>(smem);                                   // [2][RB][NS][NGC][TWP]
+    uint32_t* Lrep = reinterpret_cast<uint32_t*>(smem + C::OFF_L);               // [NTILE][RB][LW]
+    uint32_t* Ral = reinterpret_cast<uint32_t*>(smem + C::OFF_R);                // [NTILE][RB][RWT]
+    uint32_t* pk = reinterpret_cast<uint32_t*>(smem + C::OFF_PK);                // [2][RB][NS][TW]
     uint8_t* lut = smem + C::OFF_LUT;
-    constexpr int HBUF = C::H_BYTES / 8, LBUF = RB * C::LW, RBUF = C::R_BYTES / 4, PKBUF = RB * K * TW;
+    constexpr int HBUF = C::H_BYTES / 8, HROW = C::NSLOT * TWP, LBUF = RB * C::LW, RBUF = C::R_BYTES / 4, PKBUF = RB * NS * TW;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int frame = blockIdx.z / a.NC, chunk = blockIdx.z - frame * a.NC;
-    const int x0 = blockIdx.x * TW;
+    const int x0 = blockIdx.x * C::CW;
     const int yb0 = a.y0 + blockIdx.y * a.BH;
     const int yb1 = min(a.y1, yb0 + a.BH);
     const int g0 = chunk * NGC;
     if (yb0 >= yb1) return;
     // a chunk none of whose disparities is a candidate anywhere in this strip (d > X-h for every column, sad.go:64-67 + :212-218)
     // has nothing to contribute: chunk 0 always runs and writes every pixel
-    if (g0 > 0 && min(x0 + TW, a.W) - 1 - HALF < 4 * g0) return;
+    if (g0 > 0 && min(x0 + C::CW, a.W) - 1 - HALF < 4 * g0) return;
     const int r0 = yb0 - HALF;
     const int nb = ((yb1 - yb0) + 2 * HALF + RB - 1) / RB;
-    const int nvalid = a.W - (x0 - HALF);
+    // image row r0 + batch*RB + rb is row rb of `batch`; the walk of strip s starts at column x0 + 32 s - h
+    const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;              // image column of right-tile word 0 (multiple of 4)
+    const int xr0a = xr0 - (((xr0 % 16) + 16) % 16);                          // tile rows start 16-byte aligned (TMA rule), same layout without TMA
+    const int rext = (xr0 - xr0a) >> 2;                                       // words to skip at the start of a tile row
 
     for (int d = tid; d < 1040; d += C::NT) lut[d] = d <= a.D ? (uint8_t)((d * 255) / a.D) : 0;
+    for (int idx = tid; idx < 2 * PKBUF; idx += C::NT) pk[idx] = 0xFFFFFFFFu;
 
     if (warp < C::W_CONS) {
         // ======================= producer warpgroups (warps 0..11) =======================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(TMA ? C::REGS_PROD_TMA : C::REGS_PROD));
-        if (warp == C::W_FIN) {
-            // ---- finisher: min over the K partial keys of a pixel, LUT, store (batch it-2) ----
+        if (warp == C::W_LOAD || (!C::TAIL && warp == C::W_AUX)) {
+            // ---- loader (TMA, warp 11): two cp.async.bulk.tensor per batch (raw left rows, aligned right rows), completion on
+            //      an mbarrier, then the left pixels are replicated into Lrep.  Without TMA the walkers prefetch their own
+            //      rows and this warp only keeps the barrier count; so does warp 10 in the modes without a tail group. ----
             uint8_t* __restrict__ Og = a.out + (long long)frame * a.frameOut;
-            __syncthreads();
-            for (int it = 0; it < nb + 2; ++it) {
-                if (it >= 2) {
-                    const int batch = it - 2;
-                    const uint32_t* pkb = pk + (batch & 1) * PKBUF + lane;
-                    const int x = x0 + lane;
+            const int xlim = a.W - x0 - lane;                                  // column x0 + c + lane is inside the image iff c < xlim
+            const bool zero0 = x0 == 0 && lane < HALF;                          // X < h: both windows clamp, d = 0 wins (sad.go:212-218)
+            auto finish = [&](int batch) {                                      // one-strip modes: the loader warp finishes batch it-2
+                uint32_t* pkb = pk + (batch & 1) * PKBUF + lane;
+                const int row0 = r0 + batch * RB - HALF;                       // image row of item row 0
+                const int rb_lo = 2 * HALF - batch * RB, rb_hi = yb1 - row0;   // output rows of this batch: rb in [rb_lo, rb_hi)
+                uint8_t* Orow = Og + (long long)row0 * a.pitchOut + x0 + lane;
+                const long long grow = ((long long)frame * a.H + row0) * a.W + x0 + lane;       // key-map index of item row 0 (chunked ranges)
 #pragma unroll
-                    for (int rb = 0; rb < RB; ++rb) {
-                        const int rel = batch * RB + rb, y = r0 + rel - HALF;
-                        if (rel < 2 * HALF || y >= yb1 || x >= a.W) continue;
-                        uint32_t best = 0xFFFFFFFFu;
-#pragma unroll
-                        for (int k = 0; k < K; ++k) best = min(best, pkb[(rb * K + k) * TW]);
-                        if (x < HALF) best = 0;                  // sad.go:212-218: both windows clamp, d = 0 wins
-                        if (a.NC == 1) Og[(size_t)y * a.pitchOut + x] = lut[best & 0xFFFFu];
-                        else atomicMin(a.gkey + ((size_t)frame * a.H + y) * a.W + x, ((best >> 16) << 9) | (best & 511u));
-                    }
+                for (int t = 0; t < NS * RB; ++t) {
+                    const int s = t / RB, rb = t % RB;
+                    uint32_t best = pkb[(rb * NS + s) * TW];
+                    pkb[(rb * NS + s) * TW] = 0xFFFFFFFFu;                     // re-arm for the batch after next
+                    if (s == 0 && zero0) best = 0;
+                    const bool ok = rb >= rb_lo && rb < rb_hi && s * TW < xlim;
+                    if (a.NC == 1) { const uint8_t v = lut[best & 0xFFFFu]; if (ok) Orow[rb * a.pitchOut + s * TW] = v; }
+                    else if (ok) atomicMin(a.gkey + grow + rb * a.W + s * TW, ((best >> 16) << 9) | (best & 511u));
                 }
-                __syncthreads();
-            }
-        } else if (warp > C::W_FIN) {
-            // ---- warp 11: TMA tile loader (a.use_tma) — two cp.async.bulk.tensor per batch (raw left rows, aligned right
-            //      rows; hardware zero-fill outside the image), completion on an mbarrier, then the left pixels are
-            //      replicated into Lrep.  Without TMA this warp idles and the walkers prefetch their own rows. ----
-            if (TMA) {
-                uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::OFF_MBAR);
-                const uint32_t mbar0 = (uint32_t)__cvta_generic_to_shared(mbar);
-                const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;
-                const int xr0a = xr0 - (((xr0 % 16) + 16) % 16);                // 16-byte aligned start of the right tile
+            };
+            uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + C::OFF_MBAR);
+            const uint32_t mbar0 = (uint32_t)__cvta_generic_to_shared(mbar);
+            auto request = [&](int batch) {                 // two bulk tensor copies, completion counted on the buffer's mbarrier
+                const int tb = batch % C::NTILE;
+                const uint32_t bar = mbar0 + 8 * tb;
+                const uint32_t dstR = (uint32_t)__cvta_generic_to_shared(smem + C::OFF_R + tb * C::R_BYTES);
+                const uint32_t dstL = (uint32_t)__cvta_generic_to_shared(smem + C::OFF_LRAW + tb * C::LRAW_BYTES);
+                const int y = r0 + batch * RB;
+                if (lane == 0) {
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(RB * C::RWT * 4 + RB * C::LBOX) : "memory");
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                 :: "r"(dstR), "l"(&a.tmapR), "r"(xr0a), "r"(y), "r"(frame), "r"(bar) : "memory");
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                 :: "r"(dstL), "l"(&a.tmapL), "r"(x0 - HALF - C::LSH), "r"(y), "r"(frame), "r"(bar) : "memory");
+                }
+            };
+            auto complete = [&](int batch) {                // wait for the copies of `batch`, then replicate its left pixels
+                const int tb = batch % C::NTILE;
+                const uint32_t bar = mbar0 + 8 * tb;
+                // bounded wait on the phase of this buffer's (batch / NTILE)-th use; a stuck copy traps instead of hanging
+                const uint32_t parity = (uint32_t)(batch / C::NTILE) & 1u;
+                uint32_t done = 0;
+                for (int spin = 0; spin < (1 << 24) && !done; ++spin)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                if (!done) __trap();
+                // four pixels per lane and step: one (funnel-shifted) raw word -> four replicated words, one 16-byte store
+                const uint32_t* raw = reinterpret_cast<const uint32_t*>(smem + C::OFF_LRAW + tb * C::LRAW_BYTES);
+                uint4* Ld = reinterpret_cast<uint4*>(Lrep + tb * LBUF);
+                constexpr int LQ = C::LW / 4;
+                for (int idx = lane; idx < RB * LQ; idx += 32) {
+                    const int rb = idx / LQ, q = idx - rb * LQ;
+                    const uint32_t* p = raw + rb * (C::LBOX / 4) + (C::LSH >> 2) + q;
+                    uint32_t v = p[0];
+                    if (C::LSH & 3) v = __funnelshift_r(v, p[1], 8 * (C::LSH & 3));
+                    Ld[idx] = make_uint4(__byte_perm(v, 0u, 0x0000), __byte_perm(v, 0u, 0x1111), __byte_perm(v, 0u, 0x2222), __byte_perm(v, 0u, 0x3333));
+                }
+            };
+            const bool loads = TMA && warp == C::W_LOAD;
+            if (loads) {
                 if (lane == 0) {
 #pragma unroll
                     for (int t = 0; t < C::NTILE; ++t) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mbar0 + 8 * t));
                     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
                 }
                 __syncwarp();
-                auto request = [&](int batch) {                 // two bulk tensor copies, completion counted on the buffer's mbarrier
-                    const int tb = batch % C::NTILE;
-                    const uint32_t bar = mbar0 + 8 * tb;
-                    const uint32_t dstR = (uint32_t)__cvta_generic_to_shared(smem + C::OFF_R + tb * C::R_BYTES);
-                    const uint32_t dstL = (uint32_t)__cvta_generic_to_shared(smem + C::OFF_LRAW + tb * C::LRAW_BYTES);
-                    const int y = r0 + batch * RB;
-                    if (lane == 0) {
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(RB * C::RWT * 4 + RB * C::LBOX) : "memory");
-                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                                     :: "r"(dstR), "l"(&a.tmapR), "r"(xr0a), "r"(y), "r"(frame), "r"(bar) : "memory");
-                        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                                     :: "r"(dstL), "l"(&a.tmapL), "r"(x0 - HALF - C::LSH), "r"(y), "r"(frame), "r"(bar) : "memory");
-                    }
-                };
-                auto complete = [&](int batch) {                // wait for the copies of `batch`, then replicate its left pixels
-                    const int tb = batch % C::NTILE;
-                    const uint32_t bar = mbar0 + 8 * tb;
-                    // bounded wait on the phase of this buffer's (batch / NTILE)-th use; a stuck copy traps instead of hanging
-                    const uint32_t parity = (uint32_t)(batch / C::NTILE) & 1u;
-                    uint32_t done = 0;
-                    for (int spin = 0; spin < (1 << 24) && !done; ++spin)
-                        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-                    if (!done) __trap();
-                    const uint8_t* raw = smem + C::OFF_LRAW + tb * C::LRAW_BYTES;
-                    uint32_t* Ld = Lrep + tb * LBUF;
-                    for (int idx = lane; idx < RB * C::LW; idx += 32) {
-                        const int rb = idx / C::LW, i = idx - rb * C::LW;
-                        Ld[idx] = (uint32_t)raw[rb * C::LBOX + C::LSH + i] * 0x01010101u;
-                    }
-                };
                 request(0);
                 if (nb > 1) request(1);
                 if (nb > 2) request(2);
                 complete(0);
                 if (nb > 1) complete(1);
-                __syncthreads();
-                for (int it = 0; it < nb + 2; ++it) {
+            }
+            __syncthreads();
+            for (int it = 0; it < nb + 2; ++it) {
+                if (loads) {
                     if (it + 3 < nb) request(it + 3);              // buffer (it+3)%4 was last read in iteration it-1
                     if (it + 2 < nb) complete(it + 2);             // requested one iteration ago: already landed
-                    __syncthreads();
                 }
-            } else {
+                if (!C::FIN_CONS && warp == C::W_LOAD && it >= 2) finish(it - 2);
                 __syncthreads();
-                for (int it = 0; it < nb + 2; ++it) __syncthreads();
             }
         } else {
-            // ---- walkers: warp w < 9 walks row w for groups 0..31 and prefetches row w of the batch after next
-            //      (L pixels replicated, R as aligned words) into the third tile buffer; warp 9 walks group 32
-            //      of every row (one lane per row). ----
-            const bool tail = warp == C::W_TAIL;
-            const int rb = tail ? lane : warp, gl = tail ? NGC - 1 : lane;
-            const bool act = !tail || lane < RB;
+            // ---- walkers: warp w < RB walks row w; lane = (strip s, group gl) for the NGL groups the row warps take.
+            //      The tail warp walks the last group of the chunk for every (row, strip).  Without TMA a row warp also
+            //      prefetches its row of the batch after next (L pixels replicated, R as aligned words). ----
+            const bool tail = C::TAIL && warp == C::W_AUX;
+            const int ws = tail ? lane % NS : lane / NGL;                      // strip of this lane
+            const int rb = tail ? lane / NS : warp;
+            const int gl = tail ? NGC - 1 : lane - ws * NGL;
+            const bool act = tail ? lane < RB * NS : lane < NS * NGL;
+            const int nvalid = a.W - (x0 + ws * TW - HALF);                     // steps of this lane's walk inside the image
+            const bool edge = a.W - (x0 + (NS - 1) * TW - HALF) < C::NSTEP;     // warp-uniform: some strip of the CTA touches x >= W
             const uint8_t* __restrict__ Lg = a.L + (long long)frame * a.frameL;
             const uint8_t* __restrict__ Rg = a.R + (long long)frame * a.frameR;
-            const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;
-            const int xr0a = xr0 - (((xr0 % 16) + 16) % 16);                    // tile rows start 16-byte aligned (TMA rule), same layout without TMA
-            const int rext = (xr0 - xr0a) >> 2;                                 // words to skip at the start of a tile row
             constexpr int NLQ = (C::LW + 31) / 32, NRQ = (C::RWT + 31) / 32;
             int lx[NLQ], rx[NRQ], rmode[NRQ];            // column of each slot of this lane; -1 / mode 0 = zero
-#pragma unroll
-            for (int q = 0; q < NLQ; ++q) {
-                const int i = lane + 32 * q, x = x0 - HALF + i;
-                lx[q] = (i < C::LW && (unsigned)x < (unsigned)a.W) ? x : -1;
-            }
-#pragma unroll
-            for (int q = 0; q < NRQ; ++q) {
-                const int j = lane + 32 * q, x = xr0a + 4 * j;
-                const bool in = j < C::RWT && x + 3 >= 0 && x < a.W;
-                rx[q] = x;
-                rmode[q] = !in ? 0 : (a.aligned && x >= 0 && x + 3 < a.W) ? 1 : 2;
-            }
             uint32_t vl[NLQ], vr[NRQ];
+            const bool self_load = !tail && !TMA;
+            if (self_load) {
+#pragma unroll
+                for (int q = 0; q < NLQ; ++q) {
+                    const int i = lane + 32 * q, x = x0 - HALF + i;
+                    lx[q] = (i < C::LW && (unsigned)x < (unsigned)a.W) ? x : -1;
+                }
+#pragma unroll
+                for (int q = 0; q < NRQ; ++q) {
+                    const int j = lane + 32 * q, x = xr0a + 4 * j;
+                    const bool in = j < C::RWT && x + 3 >= 0 && x < a.W;
+                    rx[q] = x;
+                    rmode[q] = !in ? 0 : (a.aligned && x >= 0 && x + 3 < a.W) ? 1 : 2;
+                }
+            }
             auto issue = [&](int batch) {               // global loads of row rb of `batch` (warp-uniform row test)
                 const int y = r0 + batch * RB + rb;
                 const bool yin = (unsigned)y < (unsigned)a.H;
@@ -321,48 +373,38 @@ __global__ void __launch_bounds__(WsCfg<HALF>::NT, 1) sad_ws_kernel(const __grid
 #pragma unroll
                 for (int q = 0; q < NRQ; ++q) { const int j = lane + 32 * q; if (j < C::RWT) Rd[j] = vr[q]; }
             };
-            const bool self_load = !tail && !TMA;
             if (self_load) {
                 issue(0); commit(0);
                 if (nb > 1) { issue(1); commit(1); }
             }
             __syncthreads();
-            long long tw = 0, tc = 0, tb = 0, cprev = 0;
             for (int it = 0; it < nb + 2; ++it) {
-                if (a.debug_skip & 4) { volatile uint8_t* vq = lut; tw += (long long)(vq[0] & 0) ; }   // forces the deferred barrier wait to complete
-                const long long c0 = clock64();
-                if ((a.debug_skip & 4) && it > 0) tb += c0 - cprev;
                 const bool pre = self_load && it + 2 < nb;
                 if (pre) issue(it + 2);
-                if (it < nb && act && (a.debug_skip & 3) != 1) {
+                if (it < nb && act) {
                     const int buf = it & 1, tb = it % C::NTILE;
-                    const uint32_t* Lr = Lrep + tb * LBUF + rb * C::LW;
-                    const uint32_t* Rr = Ral + tb * RBUF + rb * C::RWT + rext + (NGC - 1 - gl);
-                    uint2* Hout = Hs + buf * HBUF + (rb * NGC + gl) * TWP;
-                    if (nvalid >= C::NSTEP) ws_walk<HALF, false>(Lr, Rr, Hout, nvalid);
-                    else                    ws_walk<HALF, true>(Lr, Rr, Hout, nvalid);
+                    const uint32_t* Lr = Lrep + tb * LBUF + rb * C::LW + ws * TW;
+                    const uint32_t* Rr = Ral + tb * RBUF + rb * C::RWT + rext + (NGC - 1 - gl) + ws * (TW / 4);
+                    uint2* Hout = Hs + buf * HBUF + rb * HROW + (ws * NGC + gl) * TWP;
+                    if (!edge) sad_walk<HALF, TW, false>(Lr, Rr, Hout, nvalid);
+                    else       sad_walk<HALF, TW, true>(Lr, Rr, Hout, nvalid);
                 }
-                const long long c1 = clock64();
-                if (pre) commit(it + 2);               // tile buffer (it+2)%3 was last read in iteration it-1
-                const long long c2 = clock64();
+                if (pre) commit(it + 2);               // tile buffer (it+2)%4 was last read in iteration it-2
                 __syncthreads();
-                if (a.debug_skip & 4) { tw += c1 - c0; tc += c2 - c1; cprev = c2; }
-            }
-            if ((a.debug_skip & 4) && lane == 0 && blockIdx.x == 7 && blockIdx.y == 0 && blockIdx.z == 0) {
-                a.gkey[warp * 4 + 0] = (uint32_t)tw; a.gkey[warp * 4 + 1] = (uint32_t)tc; a.gkey[warp * 4 + 2] = (uint32_t)tb; a.gkey[warp * 4 + 3] = nb;
             }
         }
     } else {
         // ======================= consumer warpgroups (warps 12..23) =======================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(TMA ? C::REGS_CONS_TMA : C::REGS_CONS));
         __syncthreads();
+        // ---- consumers: vertical running sums (register ring) + argmin keys for 2 or 3 groups x 32 columns ----
         const int kB = warp - C::W_CONS;
-        if (kB < K) {
-            // ---- consumers: vertical running sums (register ring) + argmin keys for GT groups x 32 columns ----
-            ws_consume<HALF, GT>(a, Hs, pk, kB, lane, x0, g0, r0, nb);
-        } else {
-            for (int it = 0; it < nb + 2; ++it) __syncthreads();       // spare warp of the consumer register class
-        }
+        WsShare sh = ws_share(MODE, 0);
+#pragma unroll
+        for (int k = 1; k < C::K; ++k)
+            if (k == kB) sh = ws_share(MODE, k);
+        if (sh.ng == 3) ws_consume<HALF, MODE, 3>(a, Hs, pk, lut, kB, sh.strip, sh.first, lane, frame, x0, g0, r0, yb1, nb);
+        else            ws_consume<HALF, MODE, 2>(a, Hs, pk, lut, kB, sh.strip, sh.first, lane, frame, x0, g0, r0, yb1, nb);
     }
 }
 

@@ -2,20 +2,26 @@
 // device buffers, the launch planner and the kernel dispatch.  No CPU fallback exists: every
 // compute entry point ends in a kernel launch or an error code.
 #include "../../include/sadgpu.h"
-#include "sad_kernels.cuh"
+#include "sad_common.cuh"
 #include "sad_fast.cuh"
 #include "sad_ws.cuh"
 #include "sad_wide.cuh"
-#include "sad_vh.cuh"
 #include "sad_ring.cuh"
+#ifdef SADGPU_DEV_VARIANTS          // developer builds only: the first correct kernel and the vertical-first experiment (cross-checks)
+#include "sad_kernels.cuh"
+#include "sad_vh.cuh"
+#endif
 #include "gray_kernels.cuh"
 
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <condition_variable>
 #include <functional>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -26,8 +32,6 @@ using namespace sadgpu;
 namespace {
 
 constexpr int kSmemBudget = 232448;      // 227 KB opt-in dynamic shared memory per CTA on sm_100
-constexpr int kGT = 5;                   // disparity groups per phase-B thread
-constexpr int kMaxThreadsPerColumn = 4;  // K: phase-B threads per pixel column
 constexpr int kMaxDevices = 64;
 
 // Developer builds (-DSADGPU_DEV_H0=7 -DSADGPU_DEV_H1=15) instantiate the kernels of two half-windows only: seconds, not minutes.
@@ -40,15 +44,6 @@ constexpr bool dev_on(int half)
 #endif
 }
 
-struct Plan {
-    SadArgs a;
-    dim3 grid;
-    int nthreads;
-    size_t smem;
-    int half;
-    int launches;
-};
-
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
@@ -60,100 +55,11 @@ int validate(int w, int h, int B, int D, int y0, int y1)
     return SADGPU_OK;
 }
 
-// Chooses tile geometry.  All quantities are documented in DESIGN.md §3.
-int make_plan(int w, int h, int B, int D, int y0, int y1, const sadgpu_tuning* t, int sm_count, Plan* p)
-{
-    int rc = validate(w, h, B, D, y0, y1);
-    if (rc) return rc;
-    SadArgs& a = p->a;
-    memset(&a, 0, sizeof(a));
-    const int half = B / 2, WIN = 2 * half + 1;
-    p->half = half;
-    a.W = w; a.H = h; a.y0 = y0; a.y1 = y1; a.D = D;
-    a.NG = (D + 4) / 4;                                   // groups of 4 disparities covering 0..D
-    int maxg = kGT * kMaxThreadsPerColumn;
-    if (t && t->groups_per_chunk > 0) maxg = std::min(maxg, t->groups_per_chunk);
-    a.NSTEP = 64;
-    a.TW = a.NSTEP - 2 * half;
-    a.TWp = round_up(a.TW, 32);
-    int RBmax = 0;
-    for (;; --maxg) {
-        if (maxg < 1) return SADGPU_EINVAL;
-        a.NC = ceil_div(a.NG, maxg);
-        a.NGc = ceil_div(a.NG, a.NC);
-        a.K = ceil_div(a.NGc, kGT);
-        a.NGP = a.NGc | 1;                                // odd stride: conflict-free 64-bit column reads
-        a.RW = a.NGc + a.NSTEP / 4;
-        const int ringrow = a.TW * a.NGP * 8;
-        const int perrow = ringrow + a.NSTEP * 4 + a.RW * 4 + a.K * a.TW * 4;
-        const int fixed = WIN * ringrow + round_up(4 * a.NG, 16) + 64;
-        RBmax = (kSmemBudget - fixed) / perrow;
-        if (RBmax >= 4) break;
-    }
-    a.RB = std::min(RBmax, 16);
-    if (t && t->rows_per_batch > 0) a.RB = std::min(RBmax, t->rows_per_batch);
-    a.NR = a.RB + WIN;
-    const int ringrow = a.TW * a.NGP * 8;
-    a.offL = round_up(a.NR * ringrow, 16);
-    a.offR = a.offL + a.RB * a.NSTEP * 4;
-    a.offPk = a.offR + a.RB * a.RW * 4;
-    a.offLut = a.offPk + a.RB * a.K * a.TW * 4;
-    p->smem = (size_t)a.offLut + round_up(4 * a.NG, 16);
-    if (p->smem > (size_t)kSmemBudget) return SADGPU_EINVAL;
-    p->nthreads = 256;
-    if (a.TWp * a.K > p->nthreads) return SADGPU_EINVAL;
-
-    const int rows = y1 - y0;
-    const int nstrips = ceil_div(w, a.TW);
-    int nbands = 1;
-    if (t && t->band_rows > 0) {
-        a.BH = std::min(std::max(1, t->band_rows), std::max(rows, 1));
-        nbands = ceil_div(std::max(rows, 1), a.BH);
-    } else {
-        // minimise waves x rows-per-CTA (one CTA per SM: the H ring fills shared memory)
-        long best_cost = -1;
-        for (int nb = 1; nb <= std::max(1, std::min(rows, 256)); ++nb) {
-            const int bh = ceil_div(std::max(rows, 1), nb);
-            const long ctas = (long)nstrips * nb * a.NC;
-            const long waves = (ctas + sm_count - 1) / sm_count;
-            const long cost = waves * (round_up(bh + 2 * half, a.RB) + 2);
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; nbands = nb; }
-        }
-        a.BH = ceil_div(std::max(rows, 1), nbands);
-        nbands = ceil_div(std::max(rows, 1), a.BH);
-    }
-    p->grid = dim3(nstrips, nbands, a.NC);
-    p->launches = a.NC == 1 ? 1 : 3;
-    return SADGPU_OK;
-}
-
-template <int HALF>
-cudaError_t launch_generic(const Plan& p, cudaStream_t s, bool* attr_done)
-{
-    auto k = sad_generic_kernel<HALF, kGT>;
-    if (!*attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
-        if (e != cudaSuccess) return e;
-        *attr_done = true;
-    }
-    k<<<p.grid, p.nthreads, p.smem, s>>>(p.a);
-    return cudaGetLastError();
-}
-
-typedef cudaError_t (*launch_fn)(const Plan&, cudaStream_t, bool*);
-template <int HALF> constexpr launch_fn generic_entry()
-{
-    if constexpr (dev_on(HALF)) return launch_generic<HALF>; else return nullptr;
-}
-const launch_fn kLaunchGeneric[16] = {
-    generic_entry<0>(), generic_entry<1>(), generic_entry<2>(), generic_entry<3>(),
-    generic_entry<4>(), generic_entry<5>(), generic_entry<6>(), generic_entry<7>(),
-    generic_entry<8>(), generic_entry<9>(), generic_entry<10>(), generic_entry<11>(),
-    generic_entry<12>(), generic_entry<13>(), generic_entry<14>(), generic_entry<15>()};
-
+// kernel_variant values of sadgpu_tuning
+enum { V_AUTO = 0, V_GENERIC = 1, V_FAST = 2, V_WS = 3, V_WIDE = 4, V_VH = 5, V_RING = 6 };
 
 // ---------------------------------------------------------------------------------------
-// Fast path (sad_fast.cuh): block_size <= 15.  Template instance = (h, groups per chunk).
+// Kernel table.  Every production kernel takes FastArgs and a grid (column strips, row bands, frames x chunks).
 // ---------------------------------------------------------------------------------------
 struct FastPlan {
     FastArgs a;
@@ -162,144 +68,164 @@ struct FastPlan {
     size_t smem;
     int half, ngc, rb, tw;
     int launches;
+    int variant, mode;
+    const struct FastEntry* fe;
 };
 
+typedef cudaError_t (*fast_fn)(const FastPlan&, cudaStream_t);
+struct FastEntry { fast_fn fn; int nt, smem, rb, tw, ngc, lbox, rbox; };
+constexpr FastEntry kNoEntry{nullptr, 0, 0, 0, 0, 0, 0, 0};
+
+// cudaFuncSetAttribute is idempotent and cheap; a per-kernel once-flag keeps it off the per-frame path (one flag per
+// device would be needed if the attribute were per device, but it belongs to the function in the primary context of each
+// device, so the flag is indexed by device).
+template <class K> cudaError_t ensure_smem(K k, int bytes, std::atomic<unsigned long long>* done_mask)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done_mask->load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done_mask->fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
 template <int HALF, int NGC>
-cudaError_t launch_fast(const FastPlan& p, cudaStream_t s, bool* attr_done)
+cudaError_t launch_fast(const FastPlan& p, cudaStream_t s)
 {
     using C = FastCfg<HALF, NGC>;
     static_assert(C::SMEM <= kSmemBudget, "fast kernel does not fit shared memory");
+    static std::atomic<unsigned long long> done{0};
     auto k = sad_fast_kernel<HALF, NGC>;
-    if (!*attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return e;
-        *attr_done = true;
-    }
+    cudaError_t e = ensure_smem(k, C::SMEM, &done);
+    if (e != cudaSuccess) return e;
     k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
     return cudaGetLastError();
 }
 
-template <int HALF>
-cudaError_t launch_ws(const FastPlan& p, cudaStream_t s, bool* attr_done)
+template <int HALF, int MODE>
+cudaError_t launch_ws(const FastPlan& p, cudaStream_t s)
 {
-    using C = WsCfg<HALF>;
-    static_assert(C::SMEM <= kSmemBudget, "warp-specialised kernel does not fit shared memory");
-    if (!*attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(sad_ws_kernel<HALF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(sad_ws_kernel<HALF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return e;
-        *attr_done = true;
-    }
-    if (p.a.use_tma) sad_ws_kernel<HALF, true><<<p.grid, C::NT, C::SMEM, s>>>(p.a);
-    else             sad_ws_kernel<HALF, false><<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    using C = WsCfg<HALF, MODE>;
+    static std::atomic<unsigned long long> done_tma{0}, done_plain{0};
+    cudaError_t e = ensure_smem(sad_ws_kernel<HALF, MODE, true>, C::SMEM, &done_tma);
+    if (e == cudaSuccess) e = ensure_smem(sad_ws_kernel<HALF, MODE, false>, C::SMEM, &done_plain);
+    if (e != cudaSuccess) return e;
+    if (p.a.use_tma) sad_ws_kernel<HALF, MODE, true><<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    else             sad_ws_kernel<HALF, MODE, false><<<p.grid, C::NT, C::SMEM, s>>>(p.a);
     return cudaGetLastError();
 }
 
 template <int HALF>
-cudaError_t launch_wide(const FastPlan& p, cudaStream_t s, bool* attr_done)
+cudaError_t launch_wide(const FastPlan& p, cudaStream_t s)
 {
     using C = WideCfg<HALF>;
     static_assert(C::SMEM <= kSmemBudget, "wide kernel does not fit shared memory");
+    static std::atomic<unsigned long long> done{0};
     auto k = sad_wide_kernel<HALF>;
-    if (!*attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return e;
-        *attr_done = true;
-    }
+    cudaError_t e = ensure_smem(k, C::SMEM, &done);
+    if (e != cudaSuccess) return e;
     k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
     return cudaGetLastError();
 }
 
 template <int HALF>
-cudaError_t launch_vh(const FastPlan& p, cudaStream_t s, bool* attr_done)
-{
-    using C = VhCfg<HALF>;
-    static_assert(C::SMEM <= kSmemBudget, "vertical-first kernel does not fit shared memory");
-    auto k = sad_vh_kernel<HALF>;
-    if (!*attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return e;
-        *attr_done = true;
-    }
-    k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
-    return cudaGetLastError();
-}
-
-template <int HALF>
-cudaError_t launch_ring(const FastPlan& p, cudaStream_t s, bool* attr_done)
+cudaError_t launch_ring(const FastPlan& p, cudaStream_t s)
 {
     using C = RingCfg<HALF>;
     static_assert(C::SMEM <= kSmemBudget, "ring kernel does not fit shared memory");
+    static std::atomic<unsigned long long> done{0};
     auto k = sad_ring_kernel<HALF>;
-    if (!*attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-        if (e != cudaSuccess) return e;
-        *attr_done = true;
-    }
+    cudaError_t e = ensure_smem(k, C::SMEM, &done);
+    if (e != cudaSuccess) return e;
     k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
     return cudaGetLastError();
 }
 
-typedef cudaError_t (*fast_fn)(const FastPlan&, cudaStream_t, bool*);
-struct FastEntry { fast_fn fn; int nt, smem, rb; };
 template <int HALF, int NGC> constexpr FastEntry fast_entry()
 {
-    if constexpr (dev_on(HALF)) return FastEntry{launch_fast<HALF, NGC>, FastCfg<HALF, NGC>::NT, FastCfg<HALF, NGC>::SMEM, FastCfg<HALF, NGC>::RB};
-    else return FastEntry{nullptr, FastCfg<HALF, NGC>::NT, FastCfg<HALF, NGC>::SMEM, FastCfg<HALF, NGC>::RB};
+    using C = FastCfg<HALF, NGC>;
+    if constexpr (dev_on(HALF)) return FastEntry{launch_fast<HALF, NGC>, C::NT, C::SMEM, C::RB, C::TW, NGC, 0, 0};
+    else return kNoEntry;
 }
-template <int HALF> constexpr FastEntry ws_entry()
+template <int HALF, int MODE> constexpr FastEntry ws_entry()
 {
-    if constexpr (dev_on(HALF)) return FastEntry{launch_ws<HALF>, WsCfg<HALF>::NT, WsCfg<HALF>::SMEM, WsCfg<HALF>::RB};
-    else return FastEntry{nullptr, WsCfg<HALF>::NT, WsCfg<HALF>::SMEM, WsCfg<HALF>::RB};
+    using C = WsCfg<HALF, MODE>;
+    if constexpr (dev_on(HALF)) return FastEntry{launch_ws<HALF, MODE>, C::NT, C::SMEM, C::RB, C::CW, C::NGC, C::LBOX, C::RWT * 4};
+    else return kNoEntry;
 }
 template <int HALF> constexpr FastEntry wide_entry()
 {
-    if constexpr (dev_on(HALF)) return FastEntry{launch_wide<HALF>, WideCfg<HALF>::NT, WideCfg<HALF>::SMEM, WideCfg<HALF>::RB};
-    else return FastEntry{nullptr, WideCfg<HALF>::NT, WideCfg<HALF>::SMEM, WideCfg<HALF>::RB};
+    using C = WideCfg<HALF>;
+    if constexpr (dev_on(HALF)) return FastEntry{launch_wide<HALF>, C::NT, C::SMEM, C::RB, C::TW, C::NGC, 0, 0};
+    else return kNoEntry;
 }
 template <int HALF> constexpr FastEntry ring_entry()
 {
-    if constexpr (dev_on(HALF)) return FastEntry{launch_ring<HALF>, RingCfg<HALF>::NT, RingCfg<HALF>::SMEM, 4};
-    else return FastEntry{nullptr, RingCfg<HALF>::NT, RingCfg<HALF>::SMEM, 4};
+    using C = RingCfg<HALF>;
+    if constexpr (dev_on(HALF)) return FastEntry{launch_ring<HALF>, C::NT, C::SMEM, 4, C::TW, C::NGC, 0, 0};
+    else return kNoEntry;
 }
-template <int HALF> constexpr FastEntry vh_entry()
-{
-    if constexpr (dev_on(HALF)) return FastEntry{launch_vh<HALF>, VhCfg<HALF>::NT, VhCfg<HALF>::SMEM, VhCfg<HALF>::CROWS};
-    else return FastEntry{nullptr, VhCfg<HALF>::NT, VhCfg<HALF>::SMEM, VhCfg<HALF>::CROWS};
-}
-// index [half][slot], slot 0/1/2 = 9/17/33 groups per chunk; h >= 5 has no 33-group instance (shared memory)
-const int kFastNgc[3] = {9, 17, 33};       // h >= 5 uses 18 in slot 1 (3 groups per phase-B thread, 384 threads: no register spills)
+
+// phase-alternating kernel (sad_fast.cuh): h <= 7; slot 0/1/2 = 9 / 17 (18 for h >= 5) / 33 groups per chunk; h >= 5 has no
+// 33-group instance (shared memory)
 const FastEntry kFast[8][3] = {
     {fast_entry<0, 9>(), fast_entry<0, 17>(), fast_entry<0, 33>()},
     {fast_entry<1, 9>(), fast_entry<1, 17>(), fast_entry<1, 33>()},
     {fast_entry<2, 9>(), fast_entry<2, 17>(), fast_entry<2, 33>()},
     {fast_entry<3, 9>(), fast_entry<3, 17>(), fast_entry<3, 33>()},
     {fast_entry<4, 9>(), fast_entry<4, 17>(), fast_entry<4, 33>()},
-    {fast_entry<5, 9>(), fast_entry<5, 18>(), FastEntry{nullptr, 0, 0, 0}},
-    {fast_entry<6, 9>(), fast_entry<6, 18>(), FastEntry{nullptr, 0, 0, 0}},
-    {fast_entry<7, 9>(), fast_entry<7, 18>(), FastEntry{nullptr, 0, 0, 0}}};
+    {fast_entry<5, 9>(), fast_entry<5, 18>(), kNoEntry},
+    {fast_entry<6, 9>(), fast_entry<6, 18>(), kNoEntry},
+    {fast_entry<7, 9>(), fast_entry<7, 18>(), kNoEntry}};
 
-// slot 3 = warp-specialised kernel (sad_ws.cuh): h <= 4, 33-group chunks, 32-column strips
-const FastEntry kWs[5] = {ws_entry<0>(), ws_entry<1>(), ws_entry<2>(), ws_entry<3>(), ws_entry<4>()};
+// warp-specialised kernel (sad_ws.cuh): h <= 4; mode 0..3 = chunks of 33 / 17 / 9 / 5 groups on 1 / 2 / 3 / 6 strips per CTA
+#define WS_ROW(H) {ws_entry<H, 0>(), ws_entry<H, 1>(), ws_entry<H, 2>(), ws_entry<H, 3>()}
+const FastEntry kWs[5][4] = {WS_ROW(0), WS_ROW(1), WS_ROW(2), WS_ROW(3), WS_ROW(4)};
 
-// slot 4 = large-window kernel (sad_wide.cuh): h = 8..15, chunks of 8 groups
-#define WIDE_ENTRY(H) wide_entry<H>()
-const FastEntry kWide[8] = {WIDE_ENTRY(8), WIDE_ENTRY(9), WIDE_ENTRY(10), WIDE_ENTRY(11), WIDE_ENTRY(12), WIDE_ENTRY(13), WIDE_ENTRY(14), WIDE_ENTRY(15)};
+// large-window phase-alternating kernel (sad_wide.cuh): h = 8..15, chunks of 8 groups
+const FastEntry kWide[8] = {wide_entry<8>(), wide_entry<9>(), wide_entry<10>(), wide_entry<11>(), wide_entry<12>(), wide_entry<13>(),
+                            wide_entry<14>(), wide_entry<15>()};
 
-// slot 5 = vertical-first warp-specialised kernel (sad_vh.cuh): h = 5..15, 33-group chunks
-#define VH_ENTRY(H) vh_entry<H>()
-const FastEntry kVh[11] = {VH_ENTRY(5), VH_ENTRY(6), VH_ENTRY(7), VH_ENTRY(8), VH_ENTRY(9), VH_ENTRY(10), VH_ENTRY(11), VH_ENTRY(12),
-                           VH_ENTRY(13), VH_ENTRY(14), VH_ENTRY(15)};
-const int kVhTw[11] = {VhCfg<5>::TW, VhCfg<6>::TW, VhCfg<7>::TW, VhCfg<8>::TW, VhCfg<9>::TW, VhCfg<10>::TW, VhCfg<11>::TW, VhCfg<12>::TW,
-                       VhCfg<13>::TW, VhCfg<14>::TW, VhCfg<15>::TW};
-bool vh_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
-// slot 6 = shared-memory-ring warp-specialised kernel (sad_ring.cuh): h = 5..15, 32-column strips, chunks of 33 groups (h <= 7) or 17
+// shared-memory-ring warp-specialised kernel (sad_ring.cuh): h = 5..15, 32-column strips, chunks of 33 groups (h <= 7) or 17
 const FastEntry kRing[11] = {ring_entry<5>(), ring_entry<6>(), ring_entry<7>(), ring_entry<8>(), ring_entry<9>(), ring_entry<10>(),
                              ring_entry<11>(), ring_entry<12>(), ring_entry<13>(), ring_entry<14>(), ring_entry<15>()};
+
+#ifdef SADGPU_DEV_VARIANTS
+template <int HALF>
+cudaError_t launch_vh(const FastPlan& p, cudaStream_t s)
+{
+    using C = VhCfg<HALF>;
+    static_assert(C::SMEM <= kSmemBudget, "vertical-first kernel does not fit shared memory");
+    static std::atomic<unsigned long long> done{0};
+    auto k = sad_vh_kernel<HALF>;
+    cudaError_t e = ensure_smem(k, C::SMEM, &done);
+    if (e != cudaSuccess) return e;
+    k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    return cudaGetLastError();
+}
+template <int HALF> constexpr FastEntry vh_entry()
+{
+    using C = VhCfg<HALF>;
+    if constexpr (dev_on(HALF)) return FastEntry{launch_vh<HALF>, C::NT, C::SMEM, C::CROWS, C::TW, 33, 0, 0};
+    else return kNoEntry;
+}
+const FastEntry kVh[11] = {vh_entry<5>(), vh_entry<6>(), vh_entry<7>(), vh_entry<8>(), vh_entry<9>(), vh_entry<10>(), vh_entry<11>(),
+                           vh_entry<12>(), vh_entry<13>(), vh_entry<14>(), vh_entry<15>()};
+bool vh_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
+#else
+bool vh_supported(int) { return false; }
+#endif
+
 bool ring_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
-// Planner default, from the measured variant sweep (profiles/r01_variant_sweep.json, inputs streaming from HBM): a ring pass over
-// 33 groups costs about 1.7x a pass of the phase-alternating kernel over 18 groups, a ring pass over
-// 17 groups 1.95x a pass of the wide kernel over 8 groups; the ring kernel is chosen whenever its passes are cheaper in total.
+bool fast_supported(int B) { return B / 2 <= 7; }
+bool wide_supported(int B) { return B / 2 >= 8 && B / 2 <= 15; }
+bool ws_supported(int B) { return B / 2 <= 4; }
+
+// Planner default for block_size >= 10, from the measured variant sweep (profiles/r01_variant_sweep.json, inputs streaming
+// from HBM): a ring pass over 33 groups costs about 1.7x a pass of the phase-alternating kernel over 18 groups, a ring pass
+// over 17 groups 1.95x a pass of the wide kernel over 8 groups; the ring kernel is chosen whenever its passes are cheaper in total.
 bool ring_auto(int B, int D)
 {
     if (!ring_supported(B)) return false;
@@ -308,56 +234,98 @@ bool ring_auto(int B, int D)
     return 195 * ((ng + 16) / 17) < 100 * ((ng + 7) / 8);
 }
 
-bool vh_auto(int B, int D) { (void)B; (void)D; return false; }      // never the fastest variant (profiles/r01_variant_sweep.json)
+// Smallest warp-specialised mode whose chunk holds all ng groups (mode 0 chunks the range).
+int ws_mode_for(int ng) { return ng <= 5 ? 3 : ng <= 9 ? 2 : ng <= 17 ? 1 : 0; }
 
-bool fast_supported(int B) { return B / 2 <= 7; }
-bool wide_supported(int B) { return B / 2 >= 8 && B / 2 <= 15; }
-bool ws_supported(int B, int D) { return B / 2 <= 4 && (D + 4) / 4 > 17; }
+// Resolves (block size, disparity range, tuning) to a kernel: variant, table entry and (for the warp-specialised kernel) mode.
+int choose_kernel(int B, int D, const sadgpu_tuning* t, int* variant_out, int* mode_out, const FastEntry** fe_out)
+{
+    const int half = B / 2, ng = (D + 4) / 4;
+    int variant = t ? t->kernel_variant : V_AUTO;
+    const int gpc = t ? t->groups_per_chunk : 0;               // tests: force smaller chunks
+    if (variant < 0 || variant > 6) return SADGPU_EINVAL;
+    if (variant == V_AUTO) {
+        if (ws_supported(B)) variant = V_WS;
+        else if (ring_auto(B, D)) variant = V_RING;
+        else variant = fast_supported(B) ? V_FAST : V_WIDE;
+    }
+    int mode = 0;
+    const FastEntry* fe = nullptr;
+    switch (variant) {
+    case V_WS:
+        if (!ws_supported(B)) return SADGPU_EINVAL;
+        mode = ws_mode_for(ng);
+        if (gpc > 0) { const int forced = gpc >= 33 ? 0 : gpc >= 17 ? 1 : gpc >= 9 ? 2 : 3; mode = std::max(mode, forced); }
+        fe = &kWs[half][mode];
+        break;
+    case V_FAST: {
+        if (!fast_supported(B)) return SADGPU_EINVAL;
+        int slot = ng <= 9 ? 0 : ng <= (half >= 5 ? 18 : 17) ? 1 : 2;
+        if (gpc > 0) slot = gpc <= 9 ? 0 : gpc <= 17 ? 1 : slot;
+        if (!kFast[half][slot].fn && slot == 2) slot = 1;
+        mode = slot;
+        fe = &kFast[half][slot];
+        break;
+    }
+    case V_WIDE:
+        if (!wide_supported(B)) return SADGPU_EINVAL;
+        fe = &kWide[half - 8];
+        break;
+    case V_RING:
+        if (!ring_supported(B)) return SADGPU_EINVAL;
+        fe = &kRing[half - 5];
+        break;
+#ifdef SADGPU_DEV_VARIANTS
+    case V_VH:
+        if (!vh_supported(B)) return SADGPU_EINVAL;
+        fe = &kVh[half - 5];
+        break;
+#endif
+    default:
+        return SADGPU_EINVAL;                                  // variants 1 and 5 exist in developer builds only
+    }
+    if (!fe->fn) return SADGPU_EINVAL;                         // developer build without this instance
+    *variant_out = variant; *mode_out = mode; *fe_out = fe;
+    return SADGPU_OK;
+}
 
-int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, const sadgpu_tuning* t, int sm_count,
-                   FastPlan* p, int* slot_out, bool want_ws = false, bool want_vh = false, bool want_ring = false)
+const char* variant_name(int v)
+{
+    switch (v) { case V_GENERIC: return "generic"; case V_FAST: return "fast"; case V_WS: return "warp-specialised"; case V_WIDE: return "wide";
+                 case V_VH: return "vertical-first"; case V_RING: return "ring"; default: return "?"; }
+}
+
+int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, const sadgpu_tuning* t, int sm_count, FastPlan* p)
 {
     int rc = validate(w, h, B, D, y0, y1);
     if (rc) return rc;
-    if ((!fast_supported(B) && !wide_supported(B)) || n_frames < 1) return SADGPU_EINVAL;
+    if (n_frames < 1) return SADGPU_EINVAL;
+    const FastEntry* fe = nullptr;
+    if ((rc = choose_kernel(B, D, t, &p->variant, &p->mode, &fe))) return rc;
+    p->fe = fe;
     const int half = B / 2;
-    const bool wide = wide_supported(B);
     FastArgs& a = p->a;
     memset(&a, 0, sizeof(a));
     a.W = w; a.H = h; a.y0 = y0; a.y1 = y1; a.D = D;
     a.NG = (D + 4) / 4;
-    int slot = a.NG <= 9 ? 0 : a.NG <= (half >= 5 ? 18 : 17) ? 1 : 2;
-    if (!wide && !kFast[half][slot].fn) slot = 1;
-    if (t && t->groups_per_chunk > 0) {                     // tests: force smaller chunks
-        slot = t->groups_per_chunk <= 9 ? 0 : t->groups_per_chunk <= 17 ? 1 : slot;
-    }
-    const bool ws = !wide && want_ws && ws_supported(B, D);
-    const bool vh = want_vh && vh_supported(B);
-    if (ws) slot = 3;
-    if (wide) slot = 4;
-    const bool ring = want_ring && ring_supported(B);
-    if (vh) slot = 5;
-    if (ring) slot = 6;
-    const FastEntry& fe = ring ? kRing[half - 5] : vh ? kVh[half - 5] : wide ? kWide[half - 8] : ws ? kWs[half] : kFast[half][slot];
-    const int tw = ring ? 32 : vh ? kVhTw[half - 5] : ws ? 32 : 64;
-    p->tw = tw;
-    p->half = half; p->ngc = ring ? (half >= 8 ? 17 : 33) : vh ? 33 : wide ? 8 : ws ? 33 : (slot == 1 && half >= 5) ? 18 : kFastNgc[slot]; p->rb = fe.rb;
+    p->tw = fe->tw; p->half = half; p->ngc = fe->ngc; p->rb = fe->rb;
     a.NC = ceil_div(a.NG, p->ngc);
-    p->nthreads = fe.nt; p->smem = fe.smem;
+    p->nthreads = fe->nt; p->smem = fe->smem;
     const int rows = std::max(1, y1 - y0);
-    const int nstrips = ceil_div(w, tw);
+    const int nstrips = ceil_div(w, p->tw);
     int nbands = 1;
     if (t && t->band_rows > 0) {
         a.BH = std::min(std::max(1, t->band_rows), rows);
     } else {
+        // minimise waves x rows-per-CTA (one CTA per SM: the shared-memory rings fill it)
         long best_cost = -1;
         for (int nb = 1; nb <= std::min(rows, 64); ++nb) {
             const int bh = ceil_div(rows, nb);
             const long ctas = (long)nstrips * nb * a.NC * n_frames;
             const long waves = (ctas + sm_count - 1) / sm_count;
             // rows a CTA spends on pipeline fill and drain, beyond its band and the window halo
-            const int fill = ws ? 2 * fe.rb : (ring || vh) ? 12 : fe.rb / 2 + 2;
-            const long cost = waves * (round_up(bh + 2 * half, fe.rb) + fill);
+            const int fill = p->variant == V_WS ? 2 * fe->rb : (p->variant == V_RING || p->variant == V_VH) ? 12 : fe->rb / 2 + 2;
+            const long cost = waves * (round_up(bh + 2 * half, fe->rb) + fill);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; nbands = nb; }
         }
         a.BH = ceil_div(rows, nbands);
@@ -365,7 +333,6 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
     nbands = ceil_div(rows, a.BH);
     p->grid = dim3(nstrips, nbands, a.NC * n_frames);
     p->launches = a.NC == 1 ? 1 : 3;
-    *slot_out = slot;
     return SADGPU_OK;
 }
 
@@ -373,19 +340,18 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn lookup_encode_tiled()
+{
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
+        return (encode_tiled_fn)p;
+    cudaGetLastError();
+    return nullptr;
+}
 encode_tiled_fn get_encode_tiled()
 {
-    static encode_tiled_fn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult st;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &st) == cudaSuccess && st == cudaDriverEntryPointSuccess)
-            fn = (encode_tiled_fn)p;
-        else
-            cudaGetLastError();
-    }
+    static const encode_tiled_fn fn = lookup_encode_tiled();     // initialised once, thread-safe
     return fn;
 }
 
@@ -403,8 +369,6 @@ bool make_tmap(CUtensorMap* m, const uint8_t* base, int w, int h, size_t pitch, 
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
-
-template <int HALF> void ws_box(int* lbox, int* rbox, int* rb) { *lbox = WsCfg<HALF>::LBOX; *rbox = WsCfg<HALF>::RWT * 4; *rb = WsCfg<HALF>::RB; }
 
 // Host-side staging copies (pageable caller memory <-> pinned buffers) are memory-bound single-thread memcpys of several
 // megabytes per frame; a few helper threads cut them to a fraction.  The pool is created with the context.
@@ -485,6 +449,7 @@ struct Slot {
     int dev_index = 0, device = 0;
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t uploaded = nullptr;                            // recorded behind the H2D copies of a submit: the caller's pinned source is free again
     uint8_t *hL = nullptr, *hR = nullptr, *hOut = nullptr;     // pinned staging
     uint8_t *dL = nullptr, *dR = nullptr, *dOut = nullptr;     // device, pitched
     uint32_t* gkey = nullptr;
@@ -500,6 +465,8 @@ struct Slot {
     int nfr = 1;                                               // frames in flight
 };
 
+struct FrameEntry;
+
 }  // namespace
 
 struct sadgpu_ctx {
@@ -510,14 +477,15 @@ struct sadgpu_ctx {
     std::atomic<int> last_launches{0};
     std::mutex pool_mu;
     std::vector<std::pair<uint8_t*, size_t>> pool;
-    bool attr_done[kMaxDevices][16];
-    bool fast_attr_done[kMaxDevices][8][5];
-    bool vh_attr_done[kMaxDevices][11];
-    bool ring_attr_done[kMaxDevices][11];
     CopyPool* copier = nullptr;
-    std::vector<size_t> dev_gkey_bytes;
-    std::vector<uint32_t*> dev_gkey;       // per device scratch for sadgpu_compute_device
     std::mutex dev_mu;
+    std::vector<uint32_t*> dev_dbg;        // per device: 4 KB of developer counters (profile builds), allocated on first use
+    // frame cache of sadgpu_compute_region: chunks of one frame pair share one whole-frame GPU pass
+    std::mutex cache_mu;
+    std::condition_variable cache_cv;
+    std::vector<FrameEntry*> cache;
+    uint64_t cache_tick = 0;
+    std::atomic<long long> region_calls{0}, region_frames{0}, region_stale{0};
 };
 
 namespace {
@@ -538,104 +506,65 @@ struct Job {
     int n_frames, w, h, B, D, y0, y1;
 };
 
-// Grows the per-device key-map scratch (only needed when the disparity range is chunked).
-int ensure_gkey(sadgpu_ctx* c, int dev_index, size_t bytes, uint32_t** out)
+// Developer counters (profile builds): 4 KB per device, allocated once, never resized.
+int ensure_dbg(sadgpu_ctx* c, int dev_index, uint32_t** out)
 {
     std::lock_guard<std::mutex> g(c->dev_mu);
-    if (c->dev_gkey_bytes[dev_index] < bytes) {
-        if (c->dev_gkey[dev_index]) { cudaDeviceSynchronize(); cudaFree(c->dev_gkey[dev_index]); c->dev_gkey[dev_index] = nullptr; }
-        cudaError_t e = cudaMalloc((void**)&c->dev_gkey[dev_index], bytes);
-        if (e != cudaSuccess) { c->dev_gkey_bytes[dev_index] = 0; return (int)e; }
-        c->dev_gkey_bytes[dev_index] = bytes;
+    if (!c->dev_dbg[dev_index]) {
+        cudaError_t e = cudaMalloc((void**)&c->dev_dbg[dev_index], 4096);
+        if (e != cudaSuccess) return (int)e;
     }
-    *out = c->dev_gkey[dev_index];
+    *out = c->dev_dbg[dev_index];
     return SADGPU_OK;
 }
 
-// Enqueue one job (one frame, or a batch of frames) on stream s.  The device must be current.
-// Chooses the fast path (block_size <= 15) or the generic kernel; never a CPU path.
+// Enqueue one job (one frame, or a batch of frames) on stream s.  The device must be current.  Never a CPU path.
+// A chunked disparity range meets in a key map: the slot's own (host entry points: one per stream slot) or, for the
+// device-resident entry points, a stream-ordered allocation that lives exactly as long as this call's kernels — two calls
+// on different streams of one device never share scratch.
 int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, uint32_t* slot_gkey, cudaStream_t s, int slot_gkey_frames = 1)
 {
-    const int variant = t ? t->kernel_variant : 0;
-    if (variant < 0 || variant > 6) return SADGPU_EINVAL;
-    if (variant == 5 && !vh_supported(j.B)) return SADGPU_EINVAL;
-    if (variant == 6 && !ring_supported(j.B)) return SADGPU_EINVAL;
-    if (variant == 2 && !fast_supported(j.B)) return SADGPU_EINVAL;
-    if (variant == 3 && !ws_supported(j.B, j.D)) return SADGPU_EINVAL;
-    if (variant == 4 && !wide_supported(j.B)) return SADGPU_EINVAL;
-    const bool use_fast = variant >= 2 || (variant == 0 && (fast_supported(j.B) || wide_supported(j.B)));
-    const bool want_ws = variant == 3 || variant == 0;
-    int launches = 0;
-    if (use_fast) {
-        FastPlan p; int slot = 0;
-        int rc = make_fast_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, j.n_frames, t, c->sm_count[dev_index], &p, &slot, want_ws,
-                                variant == 5 || (variant == 0 && vh_auto(j.B, j.D)), variant == 6 || (variant == 0 && ring_auto(j.B, j.D)));
-        if (rc) return rc;
-        if (j.y1 == j.y0) return SADGPU_OK;
-        FastArgs& a = p.a;
-        a.L = j.dL; a.R = j.dR; a.out = j.dOut;
-        a.pitchL = (int)j.pitchL; a.pitchR = (int)j.pitchR; a.pitchOut = (int)j.pitchOut;
-        a.frameL = j.frameL; a.frameR = j.frameR; a.frameOut = j.frameOut;
-        a.k65536 = 65536u;
-        a.debug_skip = t ? t->reserved[1] : 0;
-        a.use_tma = 0;
-        if (slot == 3 && !(t && t->reserved[2] == 1)) {                 // reserved[2] == 1: force the non-TMA loader (tests)
-            int lbox = 0, rbox = 0, rb = 0;
-            switch (p.half) { case 0: ws_box<0>(&lbox, &rbox, &rb); break; case 1: ws_box<1>(&lbox, &rbox, &rb); break;
-                              case 2: ws_box<2>(&lbox, &rbox, &rb); break; case 3: ws_box<3>(&lbox, &rbox, &rb); break;
-                              default: ws_box<4>(&lbox, &rbox, &rb); }
-            if (make_tmap(&a.tmapL, j.dL, j.w, j.h, j.pitchL, j.frameL, j.n_frames, lbox, rb) &&
-                make_tmap(&a.tmapR, j.dR, j.w, j.h, j.pitchR, j.frameR, j.n_frames, rbox, rb))
-                a.use_tma = 1;
-        }
-        a.aligned = ((uintptr_t)j.dR % 4 == 0 && j.pitchR % 4 == 0 && j.frameR % 4 == 0) ? 1 : 0;
-        if (a.debug_skip & 4) { uint32_t* gk = nullptr; rc = ensure_gkey(c, dev_index, 4096, &gk); if (rc) return rc; a.gkey = gk; }
-        if (a.NC > 1) {
-            const size_t n = (size_t)j.n_frames * j.w * j.h;
-            uint32_t* gk = slot_gkey;
-            if (!gk || j.n_frames > slot_gkey_frames) { rc = ensure_gkey(c, dev_index, n * sizeof(uint32_t), &gk); if (rc) return rc; }
-            a.gkey = gk;
-            sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 8192), 256, 0, s>>>(gk, n, 0xFFFFFFFFu);
-        }
-        const FastEntry& fe = slot == 6 ? kRing[p.half - 5] : slot == 5 ? kVh[p.half - 5] : slot == 4 ? kWide[p.half - 8] : slot == 3 ? kWs[p.half] : kFast[p.half][slot];
-        bool* done = slot == 6 ? &c->ring_attr_done[dev_index][p.half - 5] : slot == 5 ? &c->vh_attr_done[dev_index][p.half - 5]
-                   : slot == 4 ? &c->fast_attr_done[dev_index][p.half - 8][4] : &c->fast_attr_done[dev_index][p.half][slot];
-        if (!fe.fn) return SADGPU_EINVAL;                              // developer build without this instance
-        cudaError_t e = fe.fn(p, s, done);
-        if (e != cudaSuccess) return (int)e;
-        if (a.NC > 1) {
-            dim3 g(ceil_div(j.w, 256), j.y1 - j.y0, j.n_frames);
-            sad_finalize_kernel<<<g, 256, 0, s>>>(a.gkey, j.dOut, j.w, j.h, j.y0, j.y1, (int)j.pitchOut, j.frameOut, j.D);
-            if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
-        }
-        launches = p.launches;
-    } else {
-        Plan p;
-        int rc = make_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, t, c->sm_count[dev_index], &p);
-        if (rc) return rc;
-        if (j.y1 == j.y0) return SADGPU_OK;
-        uint32_t* gk = slot_gkey;
-        if (p.a.NC > 1 && !gk) { rc = ensure_gkey(c, dev_index, (size_t)j.w * j.h * sizeof(uint32_t), &gk); if (rc) return rc; }
-        for (int f = 0; f < j.n_frames; ++f) {
-            p.a.L = j.dL + f * j.frameL; p.a.R = j.dR + f * j.frameR; p.a.out = j.dOut + f * j.frameOut;
-            p.a.pitchL = (int)j.pitchL; p.a.pitchR = (int)j.pitchR; p.a.pitchOut = (int)j.pitchOut;
-            if (p.a.NC > 1) {
-                p.a.gkey = gk;
-                const size_t n = (size_t)j.w * j.h;
-                sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 4096), 256, 0, s>>>(gk, n, 0xFFFFFFFFu);
-            }
-            if (!kLaunchGeneric[p.half]) return SADGPU_EINVAL;         // developer build without this instance
-            cudaError_t e = kLaunchGeneric[p.half](p, s, &c->attr_done[dev_index][p.half]);
-            if (e != cudaSuccess) return (int)e;
-            if (p.a.NC > 1) {
-                dim3 g(ceil_div(j.w, 256), j.y1 - j.y0, 1);
-                sad_finalize_kernel<<<g, 256, 0, s>>>(gk, p.a.out, j.w, j.h, j.y0, j.y1, (int)j.pitchOut, 0, j.D);
-                if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
-            }
-            launches += p.launches;
-        }
+    FastPlan p;
+    int rc = make_fast_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, j.n_frames, t, c->sm_count[dev_index], &p);
+    if (rc) return rc;
+    if (j.y1 == j.y0) return SADGPU_OK;
+    const FastEntry* fe = p.fe;
+    const int variant = p.variant;
+    FastArgs& a = p.a;
+    a.L = j.dL; a.R = j.dR; a.out = j.dOut;
+    a.pitchL = (int)j.pitchL; a.pitchR = (int)j.pitchR; a.pitchOut = (int)j.pitchOut;
+    a.frameL = j.frameL; a.frameR = j.frameR; a.frameOut = j.frameOut;
+    a.k65536 = 65536u;
+    a.debug_skip = t ? t->reserved[1] : 0;
+    a.use_tma = 0;
+    if (variant == V_WS && !(t && t->reserved[2] == 1)) {                 // reserved[2] == 1: force the non-TMA loader (tests)
+        if (make_tmap(&a.tmapL, j.dL, j.w, j.h, j.pitchL, j.frameL, j.n_frames, fe->lbox, fe->rb) &&
+            make_tmap(&a.tmapR, j.dR, j.w, j.h, j.pitchR, j.frameR, j.n_frames, fe->rbox, fe->rb))
+            a.use_tma = 1;
     }
-    c->last_launches.store(launches);
+    a.aligned = ((uintptr_t)j.dR % 4 == 0 && j.pitchR % 4 == 0 && j.frameR % 4 == 0) ? 1 : 0;
+    if (a.debug_skip & 4) { uint32_t* gk = nullptr; rc = ensure_dbg(c, dev_index, &gk); if (rc) return rc; a.gkey = gk; }
+    bool async_scratch = false;
+    if (a.NC > 1) {
+        const size_t n = (size_t)j.n_frames * j.w * j.h;
+        uint32_t* gk = slot_gkey;
+        if (!gk || j.n_frames > slot_gkey_frames) {
+            cudaError_t e = cudaMallocAsync((void**)&gk, n * sizeof(uint32_t), s);
+            if (e != cudaSuccess) return (int)e;
+            async_scratch = true;
+        }
+        a.gkey = gk;
+        sad_fill_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 8192), 256, 0, s>>>(gk, n, 0xFFFFFFFFu);
+    }
+    cudaError_t e = fe->fn(p, s);
+    if (e == cudaSuccess && a.NC > 1) {
+        dim3 g(ceil_div(j.w, 256), j.y1 - j.y0, j.n_frames);
+        sad_finalize_kernel<<<g, 256, 0, s>>>(a.gkey, j.dOut, j.w, j.h, j.y0, j.y1, (int)j.pitchOut, j.frameOut, j.D);
+        e = cudaGetLastError();
+    }
+    if (async_scratch) { cudaError_t e2 = cudaFreeAsync(a.gkey, s); if (e == cudaSuccess) e = e2; }   // stream-ordered: after the kernels above
+    if (e != cudaSuccess) return (int)e;
+    c->last_launches.store(p.launches);
     return SADGPU_OK;
 }
 
@@ -708,7 +637,8 @@ int submit_locked(sadgpu_ctx* c, Slot* s, const uint8_t* l, int ls, const uint8_
 // and the download of rows [y0,y1).
 int finish_submit(sadgpu_ctx* c, Slot* s, int w, int h, int B, int D, int y0, int y1, uint8_t* direct_out, int direct_stride)
 {
-    cudaError_t e = cudaSuccess;
+    cudaError_t e = cudaEventRecord(s->uploaded, s->st);     // every H2D copy of this frame is in the stream by now
+    if (e != cudaSuccess) return (int)e;
     int rc = SADGPU_OK;
     s->out_direct = direct_out != nullptr;
     if (y1 > y0) {
@@ -747,23 +677,29 @@ int wait_locked(sadgpu_ctx* c, Slot* s, uint8_t* out, int out_stride)
     return SADGPU_OK;
 }
 
-// (Re)allocates the pinned and device buffers of a slot for `cap` frame pairs of max_w x max_h.
+// (Re)allocates the pinned and device buffers of a slot for `cap` frame pairs of max_w x max_h.  The new buffers are
+// allocated first and swapped in only when every allocation succeeded: a failed grow leaves the slot as it was.
 cudaError_t alloc_slot_buffers(Slot* s, int max_w, int max_h, int cap)
 {
     const size_t img = (size_t)round_up(max_w, 256) * (size_t)max_h;
-    cudaFreeHost(s->hL); cudaFreeHost(s->hOut); cudaFree(s->dL); cudaFree(s->dOut); cudaFree(s->gkey);
-    s->hL = s->hR = s->hOut = s->dL = s->dR = s->dOut = nullptr; s->gkey = nullptr;
-    cudaGetLastError();
+    uint8_t *hL = nullptr, *hOut = nullptr, *dL = nullptr, *dOut = nullptr;
+    uint32_t* gkey = nullptr;
     // left and right live back to back (pinned and device) so that a whole frame pair is ONE DMA
-    cudaError_t e = cudaHostAlloc((void**)&s->hL, 2 * img * cap, cudaHostAllocPortable);
-    if (e == cudaSuccess) s->hR = s->hL + img;
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&s->hOut, img * cap, cudaHostAllocPortable);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->dL, 2 * img * cap);
-    if (e == cudaSuccess) s->dR = s->dL + img;
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->dOut, img * cap);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&s->gkey, (size_t)max_w * max_h * sizeof(uint32_t) * cap);
-    if (e == cudaSuccess) s->cap = cap;
-    return e;
+    cudaError_t e = cudaHostAlloc((void**)&hL, 2 * img * cap, cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&hOut, img * cap, cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dL, 2 * img * cap);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dOut, img * cap);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&gkey, (size_t)max_w * max_h * sizeof(uint32_t) * cap);
+    if (e != cudaSuccess) {
+        cudaFreeHost(hL); cudaFreeHost(hOut); cudaFree(dL); cudaFree(dOut); cudaFree(gkey);
+        cudaGetLastError();
+        return e;
+    }
+    cudaFreeHost(s->hL); cudaFreeHost(s->hOut); cudaFree(s->dL); cudaFree(s->dOut); cudaFree(s->gkey);
+    cudaGetLastError();
+    s->hL = hL; s->hR = hL + img; s->hOut = hOut; s->dL = dL; s->dR = dL + img; s->dOut = dOut; s->gkey = gkey;
+    s->cap = cap;
+    return cudaSuccess;
 }
 
 void free_slot(Slot* s)
@@ -772,14 +708,229 @@ void free_slot(Slot* s)
     cudaSetDevice(s->device);
     if (s->st) { cudaStreamSynchronize(s->st); cudaStreamDestroy(s->st); }
     if (s->done) cudaEventDestroy(s->done);
+    if (s->uploaded) cudaEventDestroy(s->uploaded);
     cudaFreeHost(s->hL); cudaFreeHost(s->hOut); cudaFreeHost(s->hRGBA);
     cudaFree(s->dL); cudaFree(s->dOut); cudaFree(s->gkey); cudaFree(s->dRGBA);
     delete s;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Frame cache of sadgpu_compute_region.  The reference's caller cuts one frame pair into up to 160 InputChunks that all
+// point at the same two images (pkg/camera/output.go:172-187, pkg/despair/sad.go:135-165).  The first chunk of a pair
+// to arrive becomes the producer: every caller that has arrived by then helps copying the pair into a pinned snapshot
+// (blocks of rows handed out by an atomic counter), the producer runs ONE whole-frame GPU pass, and every chunk slices its
+// rectangle out of the pinned result.  A chunk is served from an entry only after the rows of ITS images that influence
+// its region compared equal to the snapshot, so a caller that reuses an image object for new pixels can never see an old
+// frame's result.
+// ---------------------------------------------------------------------------------------
+constexpr int kCacheEntries = 4;
+constexpr int kStageRows = 64;          // rows of one plane per staging block
+
+struct FrameEntry {
+    Slot* slot = nullptr;
+    const uint8_t *l = nullptr, *r = nullptr;                  // key: addresses are compared, never dereferenced outside the caller's own call
+    int ls = 0, rs = 0, w = 0, h = 0, B = 0, D = 0;
+    enum State { EMPTY, STAGING, COMPUTING, READY, FAILED } state = EMPTY;
+    int rc = 0;
+    int users = 0;                                             // calls currently attached
+    long long served = 0;                                      // pixels handed out
+    uint64_t tick = 0;
+    bool stale = false;                                        // a caller's pixels differed from the snapshot: no new caller may attach
+    int nblocks = 0;
+    std::atomic<int> next_block{0}, done_blocks{0};
+};
+
+void stage_blocks(sadgpu_ctx*, FrameEntry* e, const uint8_t* l, const uint8_t* r)
+{
+    Slot* s = e->slot;
+    const int per_plane = ceil_div(e->h, kStageRows);
+    for (;;) {
+        const int b = e->next_block.fetch_add(1, std::memory_order_relaxed);
+        if (b >= e->nblocks) break;
+        const int plane = b / per_plane, y0 = (b - plane * per_plane) * kStageRows, y1 = std::min(e->h, y0 + kStageRows);
+        const uint8_t* src = (plane ? r : l) + (size_t)y0 * (plane ? e->rs : e->ls);
+        uint8_t* dst = (plane ? s->hR : s->hL) + (size_t)y0 * s->pitch;
+        const size_t sp = (size_t)(plane ? e->rs : e->ls);
+        if (sp == s->pitch && s->pitch == (size_t)e->w) memcpy(dst, src, (size_t)(y1 - y0) * e->w);
+        else for (int y = y0; y < y1; ++y) memcpy(dst + (size_t)(y - y0) * s->pitch, src + (size_t)(y - y0) * sp, (size_t)e->w);
+        e->done_blocks.fetch_add(1, std::memory_order_release);
+    }
+}
+
+// Producer: snapshot complete -> one DMA up, one whole-frame pass, one DMA down, synchronise.
+int produce_frame(sadgpu_ctx* c, FrameEntry* e)
+{
+    Slot* s = e->slot;
+    cudaError_t err = cudaSetDevice(s->device);
+    if (err != cudaSuccess) return (int)err;
+    const size_t img = s->pitch * (size_t)e->h;
+    err = cudaMemcpyAsync(s->dL, s->hL, 2 * img, cudaMemcpyHostToDevice, s->st);            // left and right planes are adjacent
+    if (err != cudaSuccess) return (int)err;
+    Job j{s->dL, s->pitch, 0, s->dR, s->pitch, 0, s->dOut, s->pitch, 0, 1, e->w, e->h, e->B, e->D, 0, e->h};
+    int rc = run_job(c, s->dev_index, j, nullptr, s->gkey, s->st);
+    if (rc) { cudaStreamSynchronize(s->st); return rc; }
+    err = cudaMemcpyAsync(s->hOut, s->dOut, img, cudaMemcpyDeviceToHost, s->st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(s->st);
+    return err == cudaSuccess ? SADGPU_OK : (int)err;
+}
+
+bool rows_match_snapshot(const FrameEntry* e, const uint8_t* l, const uint8_t* r, int ya, int yb)
+{
+    const Slot* s = e->slot;
+    for (int plane = 0; plane < 2; ++plane) {
+        const uint8_t* src = plane ? r : l;
+        const size_t sp = (size_t)(plane ? e->rs : e->ls);
+        const uint8_t* snap = plane ? s->hR : s->hL;
+        if (sp == s->pitch && s->pitch == (size_t)e->w) {
+            if (memcmp(src + (size_t)ya * sp, snap + (size_t)ya * s->pitch, (size_t)(yb - ya) * e->w)) return false;
+        } else {
+            for (int y = ya; y < yb; ++y)
+                if (memcmp(src + (size_t)y * sp, snap + (size_t)y * s->pitch, (size_t)e->w)) return false;
+        }
+    }
+    return true;
+}
+
+// Detach from an entry; an idle entry whose every pixel has been handed out (or that is stale / failed) is retired.
+void release_entry(sadgpu_ctx* c, FrameEntry* e, long long area)
+{
+    {
+        std::lock_guard<std::mutex> g(c->cache_mu);
+        e->served += area;
+        if (--e->users == 0 && (e->stale || e->state == FrameEntry::FAILED || e->served >= (long long)e->w * e->h)) {
+            e->state = FrameEntry::EMPTY; e->l = e->r = nullptr;
+        }
+    }
+    c->cache_cv.notify_all();
+}
+
+int new_cache_entry(sadgpu_ctx* c, FrameEntry** out)
+{
+    FrameEntry* e = new (std::nothrow) FrameEntry();
+    Slot* s = new (std::nothrow) Slot();
+    if (!e || !s) { delete e; delete s; return SADGPU_ENOMEM; }
+    s->dev_index = (int)(c->cache.size() % c->devices.size()); s->device = c->devices[s->dev_index];
+    cudaError_t err = cudaSetDevice(s->device);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+    if (err == cudaSuccess) err = alloc_slot_buffers(s, c->max_w, c->max_h, 1);
+    if (err != cudaSuccess) { free_slot(s); delete e; return (int)err; }
+    e->slot = s;
+    *out = e;
+    return SADGPU_OK;
+}
+
 }  // namespace
 
 extern "C" {
+
+int sadgpu_compute_region(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_t* r, int rs, int w, int h, int B, int D,
+                          int x0, int y0, int x1, int y1, uint8_t* out, int out_stride)
+{
+    if (!c || !l || !r) return SADGPU_EINVAL;
+    if (w <= 0 || h <= 0 || ls < w || rs < w) return SADGPU_EINVAL;
+    if (w > c->max_w || h > c->max_h) return SADGPU_ERANGE;
+    int rc = validate(w, h, B, D, y0, y1);
+    if (rc) return rc;
+    if (x0 < 0 || x1 > w || x0 > x1) return SADGPU_ERANGE;
+    if (x1 == x0 || y1 == y0) return SADGPU_OK;                  // empty region: nothing to write (sad.go:48-50 allocates 0 bytes)
+    if (!out || out_stride < x1 - x0) return SADGPU_EINVAL;
+    c->region_calls.fetch_add(1, std::memory_order_relaxed);
+    const int half = B / 2;
+    for (int attempt = 0;; ++attempt) {
+        FrameEntry* e = nullptr;
+        bool producer = false;
+        {
+            std::unique_lock<std::mutex> lk(c->cache_mu);
+            if (attempt < 3)                                     // a frame that keeps changing under its caller is computed privately
+                for (FrameEntry* q : c->cache)
+                    if (q->state != FrameEntry::EMPTY && q->state != FrameEntry::FAILED && !q->stale && q->l == l && q->r == r &&
+                        q->ls == ls && q->rs == rs && q->w == w && q->h == h && q->B == B && q->D == D) { e = q; break; }
+            if (e) {
+                ++e->users;
+            } else {
+                for (;;) {                                       // an idle entry: empty first, then a new one, then the least recently used
+                    for (FrameEntry* q : c->cache)
+                        if (q->users == 0 && q->state == FrameEntry::EMPTY) { e = q; break; }
+                    if (!e && (int)c->cache.size() < kCacheEntries) {
+                        if ((rc = new_cache_entry(c, &e))) return rc;
+                        c->cache.push_back(e);
+                    }
+                    if (!e)
+                        for (FrameEntry* q : c->cache)
+                            if (q->users == 0 && (!e || q->tick < e->tick)) e = q;
+                    if (e) break;
+                    c->cache_cv.wait(lk);                        // every entry is attached to a frame in flight
+                }
+                producer = true;
+                Slot* s = e->slot;
+                e->l = l; e->r = r; e->ls = ls; e->rs = rs; e->w = w; e->h = h; e->B = B; e->D = D;
+                e->state = FrameEntry::STAGING; e->rc = 0; e->users = 1; e->served = 0; e->stale = attempt >= 3;
+                s->pitch = (size_t)round_up(w, 4);
+                s->dR = s->dL + s->pitch * (size_t)h; s->hR = s->hL + s->pitch * (size_t)h;
+                e->nblocks = 2 * ceil_div(h, kStageRows);
+                e->done_blocks.store(0); e->next_block.store(0, std::memory_order_release);
+                c->region_frames.fetch_add(1, std::memory_order_relaxed);
+            }
+            e->tick = ++c->cache_tick;
+        }
+        int state;
+        if (producer) {
+            stage_blocks(c, e, l, r);
+            while (e->done_blocks.load(std::memory_order_acquire) < e->nblocks) std::this_thread::yield();      // helpers finishing their last block
+            { std::lock_guard<std::mutex> g(c->cache_mu); e->state = FrameEntry::COMPUTING; }
+            rc = produce_frame(c, e);
+            { std::lock_guard<std::mutex> g(c->cache_mu); e->rc = rc; e->state = rc ? FrameEntry::FAILED : FrameEntry::READY; state = e->state; }
+            c->cache_cv.notify_all();
+        } else {
+            {   // the snapshot is still being taken: copy blocks of it from this caller's (identical) images
+                bool staging;
+                { std::lock_guard<std::mutex> g(c->cache_mu); staging = e->state == FrameEntry::STAGING; }
+                if (staging) stage_blocks(c, e, l, r);
+            }
+            std::unique_lock<std::mutex> lk(c->cache_mu);
+            c->cache_cv.wait(lk, [&] { return e->state == FrameEntry::READY || e->state == FrameEntry::FAILED; });
+            state = e->state; rc = e->rc;
+        }
+        if (state == FrameEntry::FAILED) { release_entry(c, e, 0); return rc; }       // every chunk of the frame reports the error
+        const int ya = std::max(0, y0 - half), yb = std::min(h, y1 + half);
+        if (!producer && !rows_match_snapshot(e, l, r, ya, yb)) {
+            { std::lock_guard<std::mutex> g(c->cache_mu); e->stale = true; }
+            release_entry(c, e, 0);
+            c->region_stale.fetch_add(1, std::memory_order_relaxed);
+            continue;                                                                  // recompute from the caller's current pixels
+        }
+        const Slot* s = e->slot;
+        for (int y = y0; y < y1; ++y)                                                  // region-local rows: OutputChunk.DisparityData (sad.go:91)
+            memcpy(out + (size_t)(y - y0) * out_stride, s->hOut + (size_t)y * s->pitch + x0, (size_t)(x1 - x0));
+        release_entry(c, e, (long long)(x1 - x0) * (y1 - y0));
+        return SADGPU_OK;
+    }
+}
+
+int sadgpu_region_stats(sadgpu_ctx* c, long long* calls, long long* frames, long long* stale)
+{
+    if (!c) return SADGPU_EINVAL;
+    if (calls) *calls = c->region_calls.load();
+    if (frames) *frames = c->region_frames.load();
+    if (stale) *stale = c->region_stale.load();
+    return SADGPU_OK;
+}
+
+int sadgpu_wait_uploaded(sadgpu_ctx* c, uint64_t ticket)
+{
+    if (!c) return SADGPU_EINVAL;
+    const int stream = (int)(ticket & 0xFFFF);
+    if (stream >= (int)c->slots.size()) return SADGPU_EBUSY;
+    Slot* s = c->slots[stream];
+    std::lock_guard<std::mutex> g(s->mu);
+    if (!s->busy || s->seq != (ticket >> 16)) return SADGPU_EBUSY;
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e == cudaSuccess) e = cudaEventSynchronize(s->uploaded);
+    return e == cudaSuccess ? SADGPU_OK : (int)e;
+}
+
 
 int sadgpu_device_count(void)
 {
@@ -799,24 +950,41 @@ int sadgpu_create(const int* devices, int n_devices, int max_w, int max_h, int n
     if (ndev == 0) return SADGPU_ENODEV;
     sadgpu_ctx* c = new (std::nothrow) sadgpu_ctx();
     if (!c) return SADGPU_ENOMEM;
-    memset(c->attr_done, 0, sizeof(c->attr_done));
-    memset(c->fast_attr_done, 0, sizeof(c->fast_attr_done));
-    memset(c->vh_attr_done, 0, sizeof(c->vh_attr_done));
-    memset(c->ring_attr_done, 0, sizeof(c->ring_attr_done));
     c->max_w = max_w; c->max_h = max_h;
+    // devices == NULL: 0..n_devices-1, or the first n_devices entries of the comma-separated list in SADGPU_DEVICES
+    std::vector<int> env_list;
+    if (!devices) {
+        if (const char* env = getenv("SADGPU_DEVICES")) {
+            for (const char* q = env; *q;) {
+                char* end = nullptr;
+                const long v = strtol(q, &end, 10);
+                if (end == q) break;
+                env_list.push_back((int)v);
+                q = *end == ',' ? end + 1 : end;
+                if (*end && *end != ',') break;
+            }
+            if ((int)env_list.size() < n_devices) { delete c; return SADGPU_ERANGE; }
+        }
+    }
     for (int i = 0; i < n_devices; ++i) {
-        const int d = devices ? devices[i] : i;
+        const int d = devices ? devices[i] : env_list.empty() ? i : env_list[i];
         if (d < 0 || d >= ndev) { delete c; return SADGPU_ERANGE; }
         cudaDeviceProp prop;
         if ((e = cudaGetDeviceProperties(&prop, d)) != cudaSuccess) { delete c; return (int)e; }
         if (prop.major != 10) { delete c; return SADGPU_ENODEV; }     // sm_100a cubin only, no fallback
         c->devices.push_back(d);
         c->sm_count.push_back(prop.multiProcessorCount);
+        // key-map scratch of the device-resident entry points comes from the stream-ordered pool: keep freed blocks cached
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, d) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
     }
     c->copier = new (std::nothrow) CopyPool((int)std::min(3u, std::max(1u, std::thread::hardware_concurrency() / 4)));
     if (!c->copier) { delete c; return SADGPU_ENOMEM; }
-    c->dev_gkey.assign(n_devices, nullptr);
-    c->dev_gkey_bytes.assign(n_devices, 0);
+    c->dev_dbg.assign(n_devices, nullptr);
     const size_t pitch = (size_t)round_up(max_w, 256);
     for (int i = 0; i < n_streams; ++i) {
         Slot* s = new (std::nothrow) Slot();
@@ -826,6 +994,7 @@ int sadgpu_create(const int* devices, int n_devices, int max_w, int max_h, int n
         e = cudaSetDevice(s->device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->uploaded, cudaEventDisableTiming);
         if (e == cudaSuccess) e = alloc_slot_buffers(s, max_w, max_h, 1);
         if (e != cudaSuccess) { sadgpu_destroy(c); return (int)e; }
     }
@@ -837,8 +1006,9 @@ void sadgpu_destroy(sadgpu_ctx* c)
 {
     if (!c) return;
     for (Slot* s : c->slots) free_slot(s);
-    for (size_t i = 0; i < c->dev_gkey.size(); ++i)
-        if (c->dev_gkey[i]) { cudaSetDevice(c->devices[i]); cudaFree(c->dev_gkey[i]); }
+    for (FrameEntry* e : c->cache) { free_slot(e->slot); delete e; }
+    for (size_t i = 0; i < c->dev_dbg.size(); ++i)
+        if (c->dev_dbg[i]) { cudaSetDevice(c->devices[i]); cudaFree(c->dev_dbg[i]); }
     for (auto& r : c->pool) cudaFreeHost(r.first);
     delete c->copier;
     delete c;
@@ -990,6 +1160,7 @@ int sadgpu_submit_batch_into(sadgpu_ctx* c, int stream, int n_frames, const uint
     if (e != cudaSuccess) return (int)e;
     Job j{s->dL, (size_t)w, (long long)(2 * img), s->dL + img, (size_t)w, (long long)(2 * img), s->dOut, (size_t)w, (long long)img,
           n_frames, w, h, B, D, 0, h};
+    if ((e = cudaEventRecord(s->uploaded, s->st)) != cudaSuccess) return (int)e;
     if ((rc = run_job(c, s->dev_index, j, nullptr, s->gkey, s->st, s->cap))) { cudaStreamSynchronize(s->st); return rc; }
     e = cudaMemcpyAsync(out, s->dOut, img * n_frames, cudaMemcpyDeviceToHost, s->st);
     if (e == cudaSuccess) e = cudaEventRecord(s->done, s->st);
@@ -1114,10 +1285,10 @@ void sadgpu_host_free(sadgpu_ctx* c, void* p)
 int sadgpu_debug_read(sadgpu_ctx* c, int device, uint32_t* host, int n_words)
 {
     if (!c || !host || device < 0 || device >= (int)c->devices.size() || n_words < 0) return SADGPU_EINVAL;
-    if (!c->dev_gkey[device] || c->dev_gkey_bytes[device] < (size_t)n_words * 4) return SADGPU_ERANGE;
+    if (!c->dev_dbg[device] || n_words > 1024) return SADGPU_ERANGE;
     cudaError_t e = cudaSetDevice(c->devices[device]);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    if (e == cudaSuccess) e = cudaMemcpy(host, c->dev_gkey[device], (size_t)n_words * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(host, c->dev_dbg[device], (size_t)n_words * 4, cudaMemcpyDeviceToHost);
     return e == cudaSuccess ? SADGPU_OK : (int)e;
 }
 
@@ -1125,34 +1296,16 @@ int sadgpu_last_launch_count(sadgpu_ctx* c) { return c ? c->last_launches.load()
 
 int sadgpu_plan_describe(int w, int h, int B, int D, int y0, int y1, const sadgpu_tuning* t, char* buf, size_t buflen)
 {
-    const int variant = t ? t->kernel_variant : 0;
-    if (variant > 6 || (variant == 2 && !fast_supported(B)) || (variant == 4 && !wide_supported(B)) || (variant == 5 && !vh_supported(B)) ||
-        (variant == 6 && !ring_supported(B)))
-        return SADGPU_EINVAL;
-    if (variant >= 2 || (variant == 0 && (fast_supported(B) || wide_supported(B)))) {
-        FastPlan p; int slot = 0;
-        const int nf = t && t->reserved[0] > 0 ? t->reserved[0] : 1;       // reserved[0]: frames per launch (describe only)
-        int rc = make_fast_plan(w, h, B, D, y0, y1, nf, t, 148, &p, &slot, variant == 3 || variant == 0,
-                                variant == 5 || (variant == 0 && vh_auto(B, D)), variant == 6 || (variant == 0 && ring_auto(B, D)));
-        if (rc) return rc;
-        if (variant == 3 && slot != 3) return SADGPU_EINVAL;
-        if (buf && buflen)
-            snprintf(buf, buflen,
-                     "{\"variant\":\"%s\",\"half\":%d,\"NG\":%d,\"NC\":%d,\"NGc\":%d,\"TW\":%d,\"RB\":%d,\"BH\":%d,"
-                     "\"grid\":[%u,%u,%u],\"threads\":%d,\"smem\":%zu,\"launches\":%d,\"frames_per_launch\":%d}",
-                     slot == 6 ? "ring" : slot == 5 ? "vertical-first" : slot == 4 ? "wide" : slot == 3 ? "warp-specialised" : "fast", p.half, p.a.NG, p.a.NC, p.ngc, p.tw, p.rb, p.a.BH,
-                     p.grid.x, p.grid.y, p.grid.z, p.nthreads, p.smem, p.launches, nf);
-        return SADGPU_OK;
-    }
-    Plan p;
-    int rc = make_plan(w, h, B, D, y0, y1, t, 148, &p);
+    FastPlan p;
+    const int nf = t && t->reserved[0] > 0 ? t->reserved[0] : 1;       // reserved[0]: frames per launch (describe only)
+    int rc = make_fast_plan(w, h, B, D, y0, y1, nf, t, 148, &p);
     if (rc) return rc;
     if (buf && buflen)
         snprintf(buf, buflen,
-                 "{\"variant\":\"generic\",\"half\":%d,\"NG\":%d,\"NC\":%d,\"NGc\":%d,\"K\":%d,\"TW\":%d,\"NSTEP\":%d,"
-                 "\"RB\":%d,\"NR\":%d,\"BH\":%d,\"grid\":[%u,%u,%u],\"threads\":%d,\"smem\":%zu,\"launches\":%d}",
-                 p.half, p.a.NG, p.a.NC, p.a.NGc, p.a.K, p.a.TW, p.a.NSTEP, p.a.RB, p.a.NR, p.a.BH,
-                 p.grid.x, p.grid.y, p.grid.z, p.nthreads, p.smem, p.launches);
+                 "{\"variant\":\"%s\",\"mode\":%d,\"half\":%d,\"NG\":%d,\"NC\":%d,\"NGc\":%d,\"TW\":%d,\"RB\":%d,\"BH\":%d,"
+                 "\"grid\":[%u,%u,%u],\"threads\":%d,\"smem\":%zu,\"launches\":%d,\"frames_per_launch\":%d}",
+                 variant_name(p.variant), p.mode, p.half, p.a.NG, p.a.NC, p.ngc, p.tw, p.rb, p.a.BH,
+                 p.grid.x, p.grid.y, p.grid.z, p.nthreads, p.smem, p.launches, nf);
     return SADGPU_OK;
 }
 

@@ -23,6 +23,11 @@ EXPORTS = {
     "sadgpu_destroy": (None, [c_void_p]),
     "sadgpu_compute": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_int, c_int, c_void_p, c_int]),
+    "sadgpu_compute_region": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, c_int, c_int, c_void_p, c_int]),
+    "sadgpu_region_stats": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_longlong),
+                                    ctypes.POINTER(ctypes.c_longlong)]),
+    "sadgpu_wait_uploaded": (c_int, [c_void_p, ctypes.c_uint64]),
     "sadgpu_compute_nrgba": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p, c_int]),
     "sadgpu_submit": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -12,9 +12,27 @@ def _u8_2d(a, name):
     a = np.asarray(a)
     if a.dtype != np.uint8 or a.ndim != 2:
         raise ValueError(f"{name}: expected a 2-D uint8 array (an image.Gray Pix plane)")
-    if a.strides[1] != 1:
+    if a.strides[1] != 1 or a.strides[0] < a.shape[1]:
         a = np.ascontiguousarray(a)
     return a
+
+
+def _pair(left, right):
+    l = _u8_2d(left, "left"); r = _u8_2d(right, "right")
+    if l.shape != r.shape:
+        raise N.SadGpuError(-1)     # left.Rect != right.Rect is rejected (SURVEY.md §8 deviations)
+    return l, r
+
+
+def _out_2d(out, shape, name="out"):
+    """A caller-supplied destination must be a writable uint8 plane of the frame's shape with unit column stride:
+    the C side writes shape[1] bytes per row at out.strides[0] intervals."""
+    if out is None:
+        return np.zeros(shape, np.uint8)
+    if not isinstance(out, np.ndarray) or out.dtype != np.uint8 or out.shape != tuple(shape) or out.strides[1] != 1 \
+            or out.strides[0] < shape[1] or not out.flags.writeable:
+        raise ValueError(f"{name}: expected a writable uint8 array of shape {tuple(shape)} with contiguous rows")
+    return out
 
 
 class Context:
@@ -46,16 +64,30 @@ class Context:
 
     # -- host entry points -------------------------------------------------------------
     def compute(self, left, right, block_size, max_disparity, y0=0, y1=None, stream=0, out=None):
-        l = _u8_2d(left, "left"); r = _u8_2d(right, "right")
-        if l.shape != r.shape:
-            raise N.SadGpuError(-1)     # left.Rect != right.Rect is rejected (SURVEY.md §8 deviations)
+        l, r = _pair(left, right)
         h, w = l.shape
         y1 = h if y1 is None else y1
-        if out is None:
-            out = np.zeros((h, w), np.uint8)
+        out = _out_2d(out, (h, w))
         N.check(self._L.sadgpu_compute(self._h, stream, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
                                         w, h, block_size, max_disparity, y0, y1, out.ctypes.data, out.strides[0]))
         return out
+
+    def compute_region(self, left, right, block_size, max_disparity, region, out=None):
+        """One InputChunk (sad.go:12-15): region = (x0, y0, x1, y1) in image coordinates (Go image.Rect order); returns the
+        region-local (Dy, Dx) block — OutputChunk.DisparityData.  Chunks of the same frame pair share one GPU pass."""
+        l, r = _pair(left, right)
+        h, w = l.shape
+        x0, y0, x1, y1 = region
+        out = _out_2d(out, (max(0, y1 - y0), max(0, x1 - x0)))
+        N.check(self._L.sadgpu_compute_region(self._h, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0], w, h,
+                                               block_size, max_disparity, x0, y0, x1, y1, out.ctypes.data,
+                                               out.strides[0] if out.size else max(1, x1 - x0)))
+        return out
+
+    def region_stats(self):
+        a, b, c = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_longlong()
+        N.check(self._L.sadgpu_region_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"calls": a.value, "frames": b.value, "stale": c.value}
 
     def compute_nrgba(self, left_rgba, right_rgba, block_size, max_disparity, stream=0, out=None):
         """left/right: uint8 [h][w][4] non-premultiplied RGBA (image.NRGBA.Pix); luma on the device, Go-exact."""
@@ -65,8 +97,7 @@ class Context:
         if l.strides[2] != 1 or l.strides[1] != 4: l = np.ascontiguousarray(l)
         if r.strides[2] != 1 or r.strides[1] != 4: r = np.ascontiguousarray(r)
         h, w, _ = l.shape
-        if out is None:
-            out = np.zeros((h, w), np.uint8)
+        out = _out_2d(out, (h, w))
         N.check(self._L.sadgpu_compute_nrgba(self._h, stream, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
                                               w, h, block_size, max_disparity, out.ctypes.data, out.strides[0]))
         return out
@@ -74,10 +105,12 @@ class Context:
     def submit(self, left, right, block_size, max_disparity, y0=0, y1=None, stream=0, out=None):
         """Enqueue one frame.  With `out` (an array from host_array) the result is written there by the D2H copy
         itself (sadgpu_submit_into) and wait(ticket) needs no destination."""
-        l = _u8_2d(left, "left"); r = _u8_2d(right, "right")
+        l, r = _pair(left, right)
         h, w = l.shape
         y1 = h if y1 is None else y1
         t = ctypes.c_uint64()
+        if out is not None:
+            out = _out_2d(out, (h, w))
         if out is None:
             N.check(self._L.sadgpu_submit(self._h, stream, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
                                            w, h, block_size, max_disparity, y0, y1, ctypes.byref(t)))
@@ -87,7 +120,14 @@ class Context:
                                                 ctypes.byref(t)))
         return t.value
 
+    def wait_uploaded(self, ticket):
+        """Blocks until the H2D copies of a submitted frame have run (pinned-pool inputs may be overwritten again)."""
+        N.check(self._L.sadgpu_wait_uploaded(self._h, ticket))
+
     def wait(self, ticket, out=None):
+        if out is not None:
+            if not isinstance(out, np.ndarray) or out.dtype != np.uint8 or out.ndim != 2 or out.strides[1] != 1:
+                raise ValueError("out: expected a uint8 plane with contiguous rows")
         if out is None:
             N.check(self._L.sadgpu_wait(self._h, ticket, None, 0))
         else:
@@ -103,7 +143,7 @@ class Context:
         if p.dtype != np.uint8 or p.ndim != 4 or p.shape[1] != 2 or not p.flags.c_contiguous:
             raise ValueError("pairs: expected a contiguous uint8 array [n][2][h][w]")
         n, _, h, w = p.shape
-        if out.shape != (n, h, w) or not out.flags.c_contiguous:
+        if not isinstance(out, np.ndarray) or out.dtype != np.uint8 or out.shape != (n, h, w) or not out.flags.c_contiguous:
             raise ValueError("out: expected a contiguous uint8 array [n][h][w]")
         t = ctypes.c_uint64()
         N.check(self._L.sadgpu_submit_batch_into(self._h, stream, n, p.ctypes.data, w, h, block_size, max_disparity,
@@ -111,10 +151,9 @@ class Context:
         return t.value
 
     def compute_sharded(self, left, right, block_size, max_disparity, out=None):
-        l = _u8_2d(left, "left"); r = _u8_2d(right, "right")
+        l, r = _pair(left, right)
         h, w = l.shape
-        if out is None:
-            out = np.zeros((h, w), np.uint8)
+        out = _out_2d(out, (h, w))
         N.check(self._L.sadgpu_compute_sharded(self._h, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0],
                                                 w, h, block_size, max_disparity, out.ctypes.data, out.strides[0]))
         return out

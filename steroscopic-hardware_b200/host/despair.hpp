@@ -9,20 +9,28 @@
 //   SetupConcurrentSAD(numWorkers)                     pkg/despair/sad.go:29-113
 //   RunSad(left, right, blockSize, maxDisparity)       pkg/despair/sad.go:119-169
 //   AssembleDisparityMap(out, dimensions, chunks)      pkg/despair/sad.go:172-202
+// and, for the callers either side of the path:
+//   ProcessDepthMap(left, right)                       pkg/camera/output.go:129-210 without the PNG round trips
+//   ReadFrame(port, frame) / StreamSerialPairs(...)    pkg/camera/serial.go:238-326 straight into pinned frames
 //
 // Chan<T> is a bounded MPMC queue with Go channel semantics (blocking send/recv, close drains).
-// The workers do not compute anything themselves: every chunk ends in sadgpu_compute (CUDA); there
-// is no CPU path.  Deviations from the reference are the documented ones: all
-// chunks are written by AssembleDisparityMap (the dropped-last-chunk bug of sad.go:179-184 is
-// available behind `faithful_drop` for comparison tests only), parameters are read once per chunk
-// exactly as in sad.go:51-53, invalid parameters surface as std::runtime_error where Go panics.
+// The workers do not compute anything themselves: every chunk ends in sadgpu_compute_region (CUDA);
+// the chunks of one frame pair share one whole-frame GPU pass inside the library.  There is no CPU
+// path.  Deviations from the reference are the documented ones: all chunks are written
+// by AssembleDisparityMap (the dropped-last-chunk bug of sad.go:179-184 is available behind
+// `faithful_drop` for comparison tests only), parameters are read once per chunk exactly as in
+// sad.go:51-53, and an error of the backend (block size > 31, image larger than the backend, no device)
+// surfaces as std::runtime_error from AssembleDisparityMap / RunSad where Go would panic — never as a
+// silently black map.
 #pragma once
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 struct sadgpu_ctx;
@@ -42,6 +50,13 @@ struct Gray {                           // image.Gray: Pix, Stride, Rect (Rect.M
     Rectangle Rect_;
 };
 Gray NewGray(Rectangle r);
+
+struct NRGBA {                          // image.NRGBA: what image/png yields for an 8-bit RGBA file (pkg/camera/output.go:138)
+    std::vector<uint8_t> Pix;           // 4 bytes per pixel, non-premultiplied
+    int Stride = 0;
+    Rectangle Rect_;
+};
+NRGBA NewNRGBA(Rectangle r);
 
 struct Parameters {                     // pkg/despair/params.go:34-37
     int BlockSize;
@@ -86,12 +101,17 @@ public:
         not_full_.notify_all();
     }
     size_t Cap() const { return cap_; }
+    // Error side band (the Go structs have no error field): the first backend failure of a worker is recorded on the output
+    // channel; AssembleDisparityMap reports it instead of returning a map with holes.
+    void Fail(const std::string& what) { std::lock_guard<std::mutex> l(m_); if (err_.empty()) err_ = what; }
+    std::string TakeError() { std::lock_guard<std::mutex> l(m_); std::string e; e.swap(err_); return e; }
 private:
     std::mutex m_;
     std::condition_variable not_empty_, not_full_;
     std::deque<T> q_;
     size_t cap_;
     bool closed_ = false;
+    std::string err_;
 };
 
 struct Pipeline {                       // the (chan<- InputChunk, <-chan OutputChunk) pair of SetupConcurrentSAD
@@ -100,10 +120,14 @@ struct Pipeline {                       // the (chan<- InputChunk, <-chan Output
 };
 
 // numWorkers <= 0 => hardware_concurrency*4 (sad.go:32-34); channels buffered 2*numWorkers (:36-37).
-// Worker w owns CUDA stream slot w of a shared sadgpu context (created on first use, sized max_w x max_h).
 Pipeline SetupConcurrentSAD(int numWorkers);
 Gray RunSad(const Gray& left, const Gray& right, int blockSize, int maxDisparity);
 Gray AssembleDisparityMap(Chan<OutputChunk>& outputChan, Rectangle dimensions, int chunks, bool faithful_drop = false);
+
+// OutputCamera.processDepthMap (pkg/camera/output.go:129-210) without the PNG files: the decoded colour pair goes to the GPU
+// as it is, the per-pixel color.GrayModel.Convert loop (:143-147, :158-162) runs there with Go's exact arithmetic
+// (sadgpu_compute_nrgba), parameters are the current DefaultParams() (:169).
+Gray ProcessDepthMap(const NRGBA& left, const NRGBA& right);
 
 // Video path (examples/run.stream.go:33-67 without the per-frame channel traffic): frames live in the
 // backend's pinned pool, n pairs travel per GPU call (sadgpu_submit_batch_into), up to `depth` calls are in flight.
@@ -120,6 +144,20 @@ PinnedFrames NewPinnedMaps(int n, int w, int h);
 void FreePinned(PinnedFrames& f);
 // Disparity maps of `pairs` into `maps` with the current DefaultParams(), `batch` pairs per call.
 void StreamSad(const PinnedFrames& pairs, PinnedFrames& maps, int batch, int depth = 4);
+
+// Serial ingest (pkg/camera/serial.go:238-326): a camera delivers width*height raw gray bytes per frame in reads of at most
+// 1024 bytes (:275-276).  ReadFrame lands them directly in a pinned plane — no intermediate buffer, no per-pixel SetGray
+// (:304-311).  Port::Read returns the number of bytes read (> 0) or <= 0 on error, like serial.Port.Read.
+struct Port {
+    virtual ~Port() = default;
+    virtual int Read(uint8_t* buf, int n) = 0;
+};
+bool ReadFrame(Port& port, uint8_t* pix, int w, int h);
+// Two cameras -> disparity maps: frame k+1 is read into the second pinned pair while frame k is on the GPU (the pair in
+// flight is borrowed by the upload, include/sadgpu.h).  sink(k, map) sees each w*h map in pinned memory, in order.
+// Returns the number of frames delivered (a short read on either port ends the stream).
+int StreamSerialPairs(Port& left, Port& right, int w, int h, int max_frames,
+                      const std::function<void(int, const uint8_t*)>& sink);
 
 // Tile planner of RunSad (sad.go:128-153), exposed for tests.
 std::vector<Rectangle> RunSadChunks(Rectangle dims, int numCPU);

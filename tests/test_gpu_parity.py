@@ -86,38 +86,35 @@ def test_tilings_do_not_change_pixels(torch_mod, ctx, oracle):
         W = int(rng.integers(20, 260)); H = int(rng.integers(10, 120))
         B = int(rng.integers(1, 32)); D = int(rng.choice([5, 16, 64, 128, 256]))
         L, R = synth_pair(rng, H, W, i % 5)
-        tun = dict(rows_per_batch=int(rng.integers(1, 12)), band_rows=int(rng.integers(1, 50)),
-                   groups_per_chunk=int(rng.integers(1, 21)), kernel_variant=1 if (i % 2 or B > 15) else 2)
-        if B > 15 and i % 2 == 0:
+        if B > 15:
             tun = dict(band_rows=int(rng.integers(1, 50)), kernel_variant=4)
-        if B <= 9 and D >= 68 and i % 3 == 0:
-            tun = dict(band_rows=int(rng.integers(1, 50)), kernel_variant=3)
+        elif B <= 9 and i % 2:          # warp-specialised kernel: forced chunk sizes 33 / 17 / 9 / 5 groups = every lane layout, chunked ranges
+            tun = dict(band_rows=int(rng.integers(1, 50)), groups_per_chunk=int(rng.choice([33, 17, 9, 5])), kernel_variant=3)
+        else:
+            tun = dict(band_rows=int(rng.integers(1, 50)), groups_per_chunk=int(rng.integers(1, 21)), kernel_variant=2)
         assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, tun), oracle.frame_box(L, R, B, D)), (W, H, B, D, tun)
     # the barrier-pipelined kernels: bands shorter than a burst / the window, one-row bands, bands that end mid-burst
     for i in range(40):
         W = int(rng.integers(20, 260)); H = int(rng.integers(10, 120))
         B = int(rng.integers(10, 32)); D = int(rng.choice([5, 16, 64, 128, 256]))
         L, R = synth_pair(rng, H, W, i % 5)
-        tun = dict(band_rows=int(rng.integers(1, 50)), kernel_variant=5 + i % 2)
+        tun = dict(band_rows=int(rng.integers(1, 50)), kernel_variant=6)
         assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, tun), oracle.frame_box(L, R, B, D)), (W, H, B, D, tun)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("variant", [2, 3, 4, 6])
 def test_every_kernel_variant_agrees_with_oracle(torch_mod, ctx, oracle, variant):
-    """variant 1 = generic shared-memory-ring kernel (any block size), 2 = register-ring fast path (B <= 15),
-    3 = warp-specialised double-buffered kernel (B <= 9, D >= 68), 4 = large-window kernel (B 16..31),
-    5 = vertical-first mbarrier-pipelined kernel (B 10..31), 6 = H-ring mbarrier-pipelined kernel (B 10..31)."""
+    """variant 2 = phase-alternating register-ring kernel (B <= 15), 3 = warp-specialised double-buffered kernel (B <= 9, every D:
+    1 / 2 / 3 / 5 strips per CTA), 4 = large-window kernel (B 16..31), 6 = H-ring mbarrier-pipelined kernel (B 10..31)."""
     rng = np.random.default_rng(60 + variant)
     for i in range(24):
         W = int(rng.integers(20, 400)); H = int(rng.integers(10, 100))
         if variant == 4:
             B = int(rng.integers(16, 32)); D = int(rng.choice([7, 16, 33, 64, 128, 200, 256]))
-        elif variant == 5:
-            B = int(rng.integers(10, 32)); D = int(rng.choice([7, 16, 33, 64, 128, 200, 256]))
         elif variant == 6:
             B = int(rng.integers(10, 32)); D = int(rng.choice([7, 16, 33, 64, 128, 200, 256]))
         elif variant == 3:
-            B = int(rng.integers(1, 10)); D = int(rng.choice([68, 100, 128, 129, 200, 256]))
+            B = int(rng.integers(1, 10)); D = int(rng.choice([1, 7, 16, 17, 20, 32, 33, 36, 48, 64, 65, 68, 100, 128, 129, 200, 256]))
         else:
             B = int(rng.integers(1, 16)); D = int(rng.choice([7, 16, 33, 64, 128, 200, 256]))
         L, R = synth_pair(rng, H, W, i % 5)
@@ -434,8 +431,9 @@ def test_row_band_sharding_across_devices(torch_mod, oracle):
     c.close()
 
 
-@pytest.mark.parametrize("variant,B,D", [(1, 21, 40), (2, 13, 64), (2, 9, 16), (3, 9, 128), (3, 5, 200), (4, 31, 256), (4, 16, 33),
-                                         (5, 15, 128), (5, 31, 256), (5, 20, 33), (6, 15, 256), (6, 11, 128), (6, 13, 40), (6, 31, 256), (6, 16, 64), (6, 22, 100)])
+@pytest.mark.parametrize("variant,B,D", [(2, 13, 64), (2, 9, 16), (3, 9, 128), (3, 5, 200), (3, 9, 64), (3, 7, 32), (3, 3, 16), (3, 8, 48),
+                                         (4, 31, 256), (4, 16, 33),
+                                         (6, 15, 256), (6, 11, 128), (6, 13, 40), (6, 31, 256), (6, 16, 64), (6, 22, 100)])
 def test_unaligned_pitch_and_odd_widths(torch_mod, ctx, oracle, variant, B, D):
     """Pitches that are not multiples of 4 disable the aligned 32-bit tile loads; widths that are not multiples of the
     strip width exercise the right-edge masking (sad.go:231-233) in every kernel."""
@@ -454,7 +452,8 @@ def test_tma_tile_loader_matches_plain_loader(torch_mod, ctx, oracle):
     torch = torch_mod
     rng = np.random.default_rng(33)
     st = torch.cuda.current_stream().cuda_stream
-    for (W, H, B, D, F) in [(64, 20, 9, 128, 1), (128, 37, 9, 128, 2), (320, 50, 5, 200, 3), (96, 9, 1, 68, 1), (160, 33, 8, 256, 2), (48, 70, 9, 100, 1)]:
+    for (W, H, B, D, F) in [(64, 20, 9, 128, 1), (128, 37, 9, 128, 2), (320, 50, 5, 200, 3), (96, 9, 1, 68, 1), (160, 33, 8, 256, 2), (48, 70, 9, 100, 1),
+                            (640, 48, 9, 64, 2), (208, 31, 7, 40, 1), (400, 25, 9, 32, 2), (112, 40, 5, 16, 3), (336, 19, 3, 8, 1)]:
         Ls = rng.integers(0, 256, (F, H, W), dtype=np.uint8); Rs = rng.integers(0, 256, (F, H, W), dtype=np.uint8)
         dL = torch.from_numpy(Ls).cuda(); dR = torch.from_numpy(Rs).cuda()
         for no_tma in (0, 1):
@@ -466,3 +465,183 @@ def test_tma_tile_loader_matches_plain_loader(torch_mod, ctx, oracle):
             got = dO.cpu().numpy()
             for f in range(F):
                 assert np.array_equal(got[f], oracle.frame_box(Ls[f], Rs[f], B, D)), (W, H, B, D, f, no_tma)
+
+
+UI_BLOCKS = list(range(3, 32, 2)) + [16]                 # cmd/components/control.templ:25-27 (odd 3..31) + the start-up default 16
+UI_DISPARITIES = list(range(16, 257, 16))                # control.templ:71-73
+
+
+@pytest.mark.parametrize("B", UI_BLOCKS)
+def test_full_ui_grid_with_planner_defaults(torch_mod, ctx, oracle, B):
+    """Every point of the WebUI's parameter grid through the planner's own choice of kernel, chunking and tiling (no tuning):
+    the variant / chunk switch points (D 64|68, 128|132, 200|204, 17/18/33-group slots) are all crossed.  Inputs rotate through
+    random, shifted texture, tie-heavy, 255-vs-0 and flat images."""
+    rng = np.random.default_rng(900 + B)
+    for i, D in enumerate(UI_DISPARITIES):
+        W = int(rng.integers(180, 230)); H = int(rng.integers(56, 72))
+        L, R = synth_pair(rng, H, W, (i + B) % 5)
+        assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D), oracle.frame_box(L, R, B, D)), (W, H, B, D)
+
+
+def _bands(h, chunk):
+    return [(y, min(y + chunk, h)) for y in range(0, h, chunk)]
+
+
+def test_compute_region_chunks_share_one_pass(ctx, oracle):
+    """sadgpu_compute_region: the reference's chunkings (OutputCamera row bands, output.go:172-187; RunSad tiles, sad.go:128-153)
+    through region-local buffers; all chunks of a frame pair cost ONE whole-frame GPU pass."""
+    rng = np.random.default_rng(31)
+    for (H, W, B, D) in [(480, 640, 16, 64), (270, 481, 9, 128), (96, 130, 31, 256)]:
+        L, R = synth_pair(rng, H, W, 1)
+        exp = oracle.frame_box(L, R, B, D)
+        s0 = ctx.region_stats()
+        out = np.zeros_like(L)
+        for (x0, y0, x1, y1) in oracle.output_camera_chunks(W, H, 32):
+            blk = ctx.compute_region(L, R, B, D, (x0, y0, x1, y1))
+            assert blk.shape == (y1 - y0, x1 - x0)
+            out[y0:y1, x0:x1] = blk
+        assert np.array_equal(out, exp)
+        s1 = ctx.region_stats()
+        assert s1["frames"] - s0["frames"] == 1 and s1["calls"] - s0["calls"] == len(oracle.output_camera_chunks(W, H, 32))
+        out2 = np.zeros_like(L)
+        for (x0, y0, x1, y1) in oracle.run_sad_chunks(W, H, 4):
+            out2[y0:y1, x0:x1] = ctx.compute_region(L, R, B, D, (x0, y0, x1, y1))
+        assert np.array_equal(out2, exp)
+        assert ctx.region_stats()["frames"] - s1["frames"] == 1      # the first sweep served every pixel: its entry was retired
+    # destination with a row stride larger than the region (a window of a bigger buffer), strided sources
+    big = np.zeros((40, 300), np.uint8)
+    Lw = np.zeros((96, 200), np.uint8); Rw = np.zeros((96, 200), np.uint8)
+    L, R = synth_pair(rng, 96, 130, 0)
+    Lw[:, 7:137] = L; Rw[:, 9:139] = R
+    ctx.compute_region(Lw[:, 7:137], Rw[:, 9:139], 7, 40, (11, 20, 121, 60), out=big[:, 50:160])
+    assert np.array_equal(big[:, 50:160], oracle.frame_box(L, R, 7, 40)[20:60, 11:121]) and not big[:, :50].any() and not big[:, 160:].any()
+
+
+def test_compute_region_concurrent_workers(ctx, oracle):
+    """32 worker threads (pkg/camera/output.go:37) pull the 160 bands of a 480-row frame, two frame pairs interleaved."""
+    import threading, queue
+    rng = np.random.default_rng(32)
+    H, W, B, D = 480, 640, 16, 64
+    pairs = [synth_pair(rng, H, W, 1) for _ in range(2)]
+    exps = [oracle.frame_box(L, R, B, D) for L, R in pairs]
+    outs = [np.zeros((H, W), np.uint8) for _ in pairs]
+    q = queue.Queue()
+    for (y0, y1) in _bands(H, max(1, H // 128)):
+        for k in range(2):
+            q.put((k, y0, y1))
+    errors = []
+    s0 = ctx.region_stats()
+
+    def worker():
+        try:
+            while True:
+                try:
+                    k, y0, y1 = q.get_nowait()
+                except queue.Empty:
+                    return
+                outs[k][y0:y1] = ctx.compute_region(pairs[k][0], pairs[k][1], B, D, (0, y0, W, y1))
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker) for _ in range(32)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errors, errors
+    for o, e in zip(outs, exps):
+        assert np.array_equal(o, e)
+    s1 = ctx.region_stats()
+    assert s1["calls"] - s0["calls"] == 320 and s1["frames"] - s0["frames"] == 2 and s1["stale"] == s0["stale"]
+
+
+def test_compute_region_never_serves_a_stale_frame(ctx, oracle):
+    """A caller that refills the SAME image objects with new pixels between chunks (or between frames) gets the new frame:
+    every chunk compares the rows it depends on with the snapshot before it is served from a shared pass."""
+    rng = np.random.default_rng(33)
+    H, W, B, D = 120, 200, 9, 64
+    L, R = synth_pair(rng, H, W, 1)
+    L2, R2 = synth_pair(rng, H, W, 1)
+    bands = _bands(H, 10)
+    s0 = ctx.region_stats()
+    out = np.zeros((H, W), np.uint8)
+    for (y0, y1) in bands[:5]:
+        out[y0:y1] = ctx.compute_region(L, R, B, D, (0, y0, W, y1))
+    exp_old = oracle.frame_box(L, R, B, D)
+    assert np.array_equal(out[:50], exp_old[:50])
+    L[:] = L2; R[:] = R2                                   # same objects, same addresses, new pixels
+    exp_new = oracle.frame_box(L, R, B, D)
+    for (y0, y1) in bands[5:]:
+        out[y0:y1] = ctx.compute_region(L, R, B, D, (0, y0, W, y1))
+    assert np.array_equal(out[50:], exp_new[50:])
+    s1 = ctx.region_stats()
+    assert s1["stale"] - s0["stale"] >= 1 and s1["frames"] - s0["frames"] == 2
+    # a change OUTSIDE the rows a chunk depends on does not invalidate it; a change inside the halo does
+    out[:] = 0
+    out[0:10] = ctx.compute_region(L, R, B, D, (0, 0, W, 10))
+    L[100, 5] ^= 0xFF
+    assert np.array_equal(ctx.compute_region(L, R, B, D, (0, 10, W, 20)), exp_new[10:20])
+    assert ctx.region_stats()["stale"] == s1["stale"]
+    L[23, 17] ^= 0x55                                      # row 23 is inside the h = 4 halo of rows [10, 20)
+    assert np.array_equal(ctx.compute_region(L, R, B, D, (0, 10, W, 20)), oracle.frame_box(L, R, B, D)[10:20])
+    assert ctx.region_stats()["stale"] == s1["stale"] + 1
+
+
+def test_compute_region_errors(ctx):
+    import despair
+    L = np.zeros((20, 30), np.uint8)
+    for region, B, D, code in [((0, 0, 30, 20), 33, 64, -1), ((0, 0, 30, 20), 9, 0, -1), ((0, 0, 31, 20), 9, 64, -2),
+                               ((0, 5, 30, 21), 9, 64, -2), ((4, 0, 2, 20), 9, 64, -2)]:
+        with pytest.raises(despair.SadGpuError) as e:
+            ctx.compute_region(L, L, B, D, region)
+        assert e.value.code == code, (region, B, D)
+    assert ctx.compute_region(L, L, 9, 64, (5, 5, 5, 10)).shape == (5, 0)          # empty region: nothing to do
+
+
+def test_concurrent_device_calls_with_chunked_disparity_range(torch_mod, ctx, oracle):
+    """Two host threads, two CUDA streams, ONE device, max_disparity 256 (two chunks merged through a key map): each call has
+    its own stream-ordered scratch, so concurrent calls cannot corrupt each other (round-1 advisor finding)."""
+    import threading
+    torch = torch_mod
+    rng = np.random.default_rng(34)
+    H, W, F = 200, 640, 3
+    jobs = []
+    for (B, D) in [(9, 256), (15, 256)]:
+        L = rng.integers(0, 256, (F, H, W), dtype=np.uint8); R = np.roll(L, -23, axis=2).copy()
+        R[:, ::5] = rng.integers(0, 256, (F, (H + 4) // 5, W), dtype=np.uint8)
+        exp = np.stack([oracle.frame_box(L[f], R[f], B, D) for f in range(F)])
+        jobs.append((B, D, torch.from_numpy(L).cuda(), torch.from_numpy(R).cuda(), exp))
+    torch.cuda.synchronize()
+    errors = []
+
+    def run(job):
+        B, D, dL, dR, exp = job
+        try:
+            st = torch.cuda.Stream()
+            for rep in range(12):
+                dO = torch.full((F, H, W), 99, dtype=torch.uint8, device="cuda")
+                st.wait_stream(torch.cuda.current_stream())
+                ctx.compute_device_batch(F, dL.data_ptr(), W, W * H, dR.data_ptr(), W, W * H, W, H, B, D, dO.data_ptr(), W, W * H,
+                                         cuda_stream=st.cuda_stream)
+                st.synchronize()
+                if not np.array_equal(dO.cpu().numpy(), exp):
+                    errors.append((B, D, rep))
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=run, args=(j,)) for j in jobs]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errors, errors
+
+
+def test_wait_uploaded_releases_pinned_inputs(ctx, oracle):
+    """Pinned-pool inputs are borrowed by the upload: after sadgpu_wait_uploaded the caller may refill them while the frame
+    is still on the GPU (one pinned frame per camera)."""
+    rng = np.random.default_rng(35)
+    H, W = 200, 320
+    pl, pr = ctx.host_pair(H, W); out = ctx.host_array((H, W))
+    frames = [synth_pair(rng, H, W, 1) for _ in range(4)]
+    for (L, R) in frames:
+        pl[:] = L; pr[:] = R
+        t = ctx.submit(pl, pr, 9, 128, stream=0, out=out)
+        ctx.wait_uploaded(t)
+        pl[:] = 0; pr[:] = 255                              # the next capture overwrites the frame
+        ctx.wait(t)
+        assert np.array_equal(out, oracle.frame_box(L, R, 9, 128))

@@ -174,3 +174,29 @@ def test_rgba_crop_fixture_is_pinned(oracle):
     R = load_png(os.path.join(GOLDEN, f"R_{m['tag']}_rgba_crop.png"), "intended")
     assert L.shape == (m["h"], m["w"]) and sha(L) == m["left_gray_sha256"] and sha(R) == m["right_gray_sha256"]
     assert sha(oracle.frame_box(L, R, 9, 64)) == m["b9_d64_sha256"]
+
+
+@pytest.mark.parametrize("B,D", [(9, 128), (16, 128), (31, 128), (9, 256), (16, 256), (31, 256), (15, 200), (3, 255)])
+def test_literal_equals_box_at_full_disparity_ranges(oracle, B, D):
+    """Round-1 verdict, weak #1(ii): the closed form every full-size GPU test compares with (frame_box) against the LITERAL
+    restatement of sad.go:55-95 / :205-244 at the large end of the parameter surface — W >= 400 (wider than D, so that all
+    D+1 candidates are live), D in {128, 256}, B in {9, 16, 31}, on row bands that include the top and bottom borders.
+    Images: shifted texture with noise (a true disparity), tie-heavy, and 255-vs-0 (largest sums)."""
+    rng = np.random.default_rng(1000 + B + D)
+    W, H = 420, 40
+    threads = min(8, os.cpu_count() or 1)
+    base = rng.integers(0, 256, (H, W + 300), dtype=np.uint8)
+    shift = int(rng.integers(D // 2, D))
+    L0 = np.ascontiguousarray(base[:, :W]); R0 = np.ascontiguousarray(base[:, shift:shift + W])
+    R0 = np.clip(R0.astype(np.int16) + rng.integers(-2, 3, R0.shape), 0, 255).astype(np.uint8)      # L(x) ~ R(x - shift)
+    cases = [(L0, R0), (rng.integers(0, 3, (H, W), dtype=np.uint8), rng.integers(0, 3, (H, W), dtype=np.uint8))]
+    if B >= 16:
+        cases.append((np.full((H, W), 255, np.uint8), np.zeros((H, W), np.uint8)))
+    bands = [(0, 6), (17, 23), (H - 6, H)] if B >= 16 else [(0, 10), (15, 25), (H - 10, H)]
+    for L, R in cases:
+        for (y0, y1) in bands:
+            lit = oracle.frame_literal_mt(L, R, B, D, threads=threads, y0=y0, y1=y1, early_exit=False)
+            assert np.array_equal(lit, oracle.frame_box(L, R, B, D, y0, y1)), (B, D, y0, y1)
+    # the planted disparity is what both recover in the interior (sanity of the generator, not of the oracle)
+    best = (oracle.frame_box(L0, R0, B, D, 18, 22).astype(int) * D + 254) // 255
+    assert abs(int(np.median(best[:, D + B:W - B])) - shift) <= 1

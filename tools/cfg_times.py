@@ -40,7 +40,7 @@ def main():
         r = time_cfg(ctx, W, H, B, D, F); r["name"] = name; out["configs"].append(r); print(r, flush=True)
     if "--sweep" in sys.argv:
         for B in (3, 5, 7, 9, 11, 13, 15, 16, 17, 21, 25, 31):
-            for D in (16, 64, 128, 256):
+            for D in (16, 32, 64, 128, 256):
                 r = time_cfg(ctx, 1920, 1080, B, D, 8, reps=3); out["sweep"].append(r); print(r, flush=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "cfg_times.json"), "w"), indent=1)
 

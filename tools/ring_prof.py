@@ -13,14 +13,14 @@ rng = np.random.default_rng(1)
 L = torch.from_numpy(rng.integers(0, 256, (F, H, W), dtype=np.uint8)).cuda(); R = torch.roll(L, -20, 2).contiguous(); O = torch.zeros_like(L)
 st = torch.cuda.current_stream().cuda_stream
 for flags in (0, 4):
-    t = N.Tuning(); t.kernel_variant = int(os.environ.get("VARIANT", 5)); t.reserved[1] = flags
+    t = N.Tuning(); t.kernel_variant = int(os.environ.get("VARIANT", 6)); t.reserved[1] = flags
     run = lambda: N.check(N.lib().sadgpu_compute_device_batch(ctx._h, 0, F, L.data_ptr(), W, W * H, R.data_ptr(), W, W * H, W, H, B, D, 0, H, O.data_ptr(), W, W * H, st, ctypes.byref(t)))
     for _ in range(2): run()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5): run()
     e1.record(); torch.cuda.synchronize()
-    print(f"flags {flags}: {e0.elapsed_time(e1) / 5 / F * 1e3:.1f} us/frame", despair.plan_describe(W, H, B, D, tuning=dict(kernel_variant=int(os.environ.get("VARIANT", 5))), frames=F)["grid"])
+    print(f"flags {flags}: {e0.elapsed_time(e1) / 5 / F * 1e3:.1f} us/frame", despair.plan_describe(W, H, B, D, tuning=dict(kernel_variant=int(os.environ.get("VARIANT", 6))), frames=F)["grid"])
 buf = (ctypes.c_uint32 * 192)()
 N.check(N.lib().sadgpu_debug_read(ctx._h, 0, buf, 192))
 v = np.array(buf[:], dtype=np.int64).reshape(24, 8) * 16

@@ -1,0 +1,29 @@
+"""Launches the warp-specialised kernel once per lane layout (max disparity 128 / 64 / 32 / 16, block 9, 8 frames of 1080p) for an ncu
+capture; prints CUDA-event times when run plain.  env: B (default 9), DS (comma list)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "steroscopic-hardware_b200"))
+import numpy as np, torch
+from despair import _native as N
+if os.environ.get("SADGPU_LIB"): N.LIB_PATH = os.environ["SADGPU_LIB"]
+import despair
+B = int(os.environ.get("B", 9)); DS = [int(x) for x in os.environ.get("DS", "128,64,32,16").split(",")]
+W, H, F = 1920, 1080, 8
+ctx = despair.Context([0], W, H, 1)
+rng = np.random.default_rng(1)
+if os.environ.get("CHECK"):            # developer A/B runs: a small parity check against the oracle first
+    from oracle import oracle as O
+    bad = 0
+    for D in DS:
+        for (hh, ww) in ((37, 200), (64, 333)):
+            l = rng.integers(0, 256, (hh, ww), dtype=np.uint8); r = np.roll(l, -7, 1)
+            bad += int((ctx.compute(l, r, B, D) != O.frame_box(l, r, B, D)).sum())
+    print("parity check: wrong pixels =", bad, flush=True)
+L = torch.from_numpy(rng.integers(0, 256, (F, H, W), dtype=np.uint8)).cuda(); R = torch.roll(L, -20, 2).contiguous(); O = torch.zeros_like(L)
+st = torch.cuda.current_stream().cuda_stream
+for D in DS:
+    run = lambda: ctx.compute_device_batch(F, L.data_ptr(), W, W * H, R.data_ptr(), W, W * H, W, H, B, D, O.data_ptr(), W, W * H, cuda_stream=st)
+    run(); torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); run(); e1.record(); torch.cuda.synchronize()
+    print(f"B={B} D={D}: {e0.elapsed_time(e1) / F * 1e3:.1f} us/frame", despair.plan_describe(W, H, B, D, frames=F), flush=True)
