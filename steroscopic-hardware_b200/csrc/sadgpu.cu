@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -445,6 +446,24 @@ private:
     bool stop_ = false;
 };
 
+// A few dozen nanoseconds of critical section, taken ~300 times per frame by up to 32 threads: a contended std::mutex costs a
+// system call per hand-over (1.6 us measured on the GPU hosts), a test-and-test-and-set lock 0.1 us.
+class SpinLock {
+public:
+    void lock()
+    {
+        while (b_.exchange(true, std::memory_order_acquire))
+            while (b_.load(std::memory_order_relaxed)) {
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+            }
+    }
+    void unlock() { b_.store(false, std::memory_order_release); }
+private:
+    std::atomic<bool> b_{false};
+};
+
 struct Slot {
     int dev_index = 0, device = 0;
     cudaStream_t st = nullptr;
@@ -481,8 +500,13 @@ struct sadgpu_ctx {
     std::mutex dev_mu;
     std::vector<uint32_t*> dev_dbg;        // per device: 4 KB of developer counters (profile builds), allocated on first use
     // frame cache of sadgpu_compute_region: chunks of one frame pair share one whole-frame GPU pass
-    std::mutex cache_mu;
+    SpinLock cache_mu;                     // protects the entries' bookkeeping (never held across a copy, a CUDA call or a sleep)
+    std::mutex cache_sleep_mu;             // sleepers only
     std::condition_variable cache_cv;
+    std::atomic<int> cache_sleepers{0};    // threads asleep on cache_cv (a wake-up call is only made for them)
+    std::once_flag cache_once;
+    int cache_rc = 0;
+    std::atomic<int> cache_spinners{0};    // threads polling an entry's state
     std::vector<FrameEntry*> cache;
     uint64_t cache_tick = 0;
     std::atomic<long long> region_calls{0}, region_frames{0}, region_stale{0};
@@ -731,7 +755,8 @@ struct FrameEntry {
     Slot* slot = nullptr;
     const uint8_t *l = nullptr, *r = nullptr;                  // key: addresses are compared, never dereferenced outside the caller's own call
     int ls = 0, rs = 0, w = 0, h = 0, B = 0, D = 0;
-    enum State { EMPTY, STAGING, COMPUTING, READY, FAILED } state = EMPTY;
+    enum State { EMPTY, STAGING, COMPUTING, READY, FAILED };
+    std::atomic<int> state{EMPTY};                             // written under cache_mu; waiters poll it before they sleep
     int rc = 0;
     int users = 0;                                             // calls currently attached
     long long served = 0;                                      // pixels handed out
@@ -796,13 +821,13 @@ bool rows_match_snapshot(const FrameEntry* e, const uint8_t* l, const uint8_t* r
 void release_entry(sadgpu_ctx* c, FrameEntry* e, long long area)
 {
     {
-        std::lock_guard<std::mutex> g(c->cache_mu);
+        std::lock_guard<SpinLock> g(c->cache_mu);
         e->served += area;
         if (--e->users == 0 && (e->stale || e->state == FrameEntry::FAILED || e->served >= (long long)e->w * e->h)) {
             e->state = FrameEntry::EMPTY; e->l = e->r = nullptr;
         }
     }
-    c->cache_cv.notify_all();
+    if (c->cache_sleepers.load(std::memory_order_seq_cst) > 0) { std::lock_guard<std::mutex> g(c->cache_sleep_mu); c->cache_cv.notify_all(); }
 }
 
 int new_cache_entry(sadgpu_ctx* c, FrameEntry** out)
@@ -837,12 +862,19 @@ int sadgpu_compute_region(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_t
     if (x1 == x0 || y1 == y0) return SADGPU_OK;                  // empty region: nothing to write (sad.go:48-50 allocates 0 bytes)
     if (!out || out_stride < x1 - x0) return SADGPU_EINVAL;
     c->region_calls.fetch_add(1, std::memory_order_relaxed);
+    std::call_once(c->cache_once, [c] {                          // the entries' pinned and device buffers: once, outside every lock
+        for (int i = 0; i < kCacheEntries && !c->cache_rc; ++i) {
+            FrameEntry* fresh = nullptr;
+            if ((c->cache_rc = new_cache_entry(c, &fresh)) == SADGPU_OK) c->cache.push_back(fresh);
+        }
+    });
+    if (c->cache.empty()) return c->cache_rc ? c->cache_rc : SADGPU_ENOMEM;
     const int half = B / 2;
     for (int attempt = 0;; ++attempt) {
         FrameEntry* e = nullptr;
         bool producer = false;
         {
-            std::unique_lock<std::mutex> lk(c->cache_mu);
+            std::unique_lock<SpinLock> lk(c->cache_mu);
             if (attempt < 3)                                     // a frame that keeps changing under its caller is computed privately
                 for (FrameEntry* q : c->cache)
                     if (q->state != FrameEntry::EMPTY && q->state != FrameEntry::FAILED && !q->stale && q->l == l && q->r == r &&
@@ -850,18 +882,21 @@ int sadgpu_compute_region(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_t
             if (e) {
                 ++e->users;
             } else {
-                for (;;) {                                       // an idle entry: empty first, then a new one, then the least recently used
+                for (;;) {                                       // an idle entry: empty first, then the least recently used
                     for (FrameEntry* q : c->cache)
                         if (q->users == 0 && q->state == FrameEntry::EMPTY) { e = q; break; }
-                    if (!e && (int)c->cache.size() < kCacheEntries) {
-                        if ((rc = new_cache_entry(c, &e))) return rc;
-                        c->cache.push_back(e);
-                    }
                     if (!e)
                         for (FrameEntry* q : c->cache)
                             if (q->users == 0 && (!e || q->tick < e->tick)) e = q;
                     if (e) break;
-                    c->cache_cv.wait(lk);                        // every entry is attached to a frame in flight
+                    lk.unlock();                                 // every entry is attached to a frame in flight: doze until one is released
+                    {
+                        std::unique_lock<std::mutex> sl(c->cache_sleep_mu);
+                        c->cache_sleepers.fetch_add(1, std::memory_order_seq_cst);
+                        c->cache_cv.wait_for(sl, std::chrono::microseconds(100));
+                        c->cache_sleepers.fetch_sub(1, std::memory_order_seq_cst);
+                    }
+                    lk.lock();
                 }
                 producer = true;
                 Slot* s = e->slot;
@@ -876,31 +911,56 @@ int sadgpu_compute_region(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_t
             e->tick = ++c->cache_tick;
         }
         int state;
+        const int ya = std::max(0, y0 - half), yb = std::min(h, y1 + half);
         if (producer) {
             stage_blocks(c, e, l, r);
             while (e->done_blocks.load(std::memory_order_acquire) < e->nblocks) std::this_thread::yield();      // helpers finishing their last block
-            { std::lock_guard<std::mutex> g(c->cache_mu); e->state = FrameEntry::COMPUTING; }
+            e->state.store(FrameEntry::COMPUTING, std::memory_order_release);            // the snapshot is complete: waiters may compare
             rc = produce_frame(c, e);
-            { std::lock_guard<std::mutex> g(c->cache_mu); e->rc = rc; e->state = rc ? FrameEntry::FAILED : FrameEntry::READY; state = e->state; }
-            c->cache_cv.notify_all();
-        } else {
-            {   // the snapshot is still being taken: copy blocks of it from this caller's (identical) images
-                bool staging;
-                { std::lock_guard<std::mutex> g(c->cache_mu); staging = e->state == FrameEntry::STAGING; }
-                if (staging) stage_blocks(c, e, l, r);
+            {
+                std::lock_guard<SpinLock> g(c->cache_mu);
+                e->rc = rc; e->state = rc ? FrameEntry::FAILED : FrameEntry::READY; state = e->state;
             }
-            std::unique_lock<std::mutex> lk(c->cache_mu);
-            c->cache_cv.wait(lk, [&] { return e->state == FrameEntry::READY || e->state == FrameEntry::FAILED; });
-            state = e->state; rc = e->rc;
+            if (c->cache_sleepers.load(std::memory_order_seq_cst) > 0) { std::lock_guard<std::mutex> g(c->cache_sleep_mu); c->cache_cv.notify_all(); }
+        } else {
+            // the snapshot is still being taken: copy blocks of it from this caller's (identical) images
+            if (e->state.load(std::memory_order_acquire) == FrameEntry::STAGING) stage_blocks(c, e, l, r);
+            // A whole-frame pass takes 0.1 .. 3 ms: poll for a while (waking sleeping workers costs more than the pass of a small
+            // frame), then sleep.  Two stops: snapshot complete (the rows this chunk depends on are compared with it while the
+            // GPU works), then result ready.
+            auto wait_for = [&](auto reached) {
+                if (reached()) return;
+                static const int spin_limit = std::max(1, (int)std::thread::hardware_concurrency() / 2 - 1);   // never more pollers than half the cores
+                if (c->cache_spinners.fetch_add(1, std::memory_order_relaxed) < spin_limit) {
+                    const auto t0 = std::chrono::steady_clock::now();
+                    while (!reached() && std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(400)) {
+                        for (int i = 0; i < 64 && !reached(); ++i) {
+#if defined(__x86_64__) || defined(__i386__)
+                            __builtin_ia32_pause();
+#endif
+                        }
+                    }
+                }
+                c->cache_spinners.fetch_sub(1, std::memory_order_relaxed);
+                if (reached()) return;
+                std::unique_lock<std::mutex> lk(c->cache_sleep_mu);
+                // the producer leaves STAGING without a wake-up call: sleepers re-check every 50 us until the result is there
+                c->cache_sleepers.fetch_add(1, std::memory_order_seq_cst);
+                while (!reached()) c->cache_cv.wait_for(lk, std::chrono::microseconds(50));
+                c->cache_sleepers.fetch_sub(1, std::memory_order_seq_cst);
+            };
+            wait_for([&] { return e->state.load(std::memory_order_acquire) != FrameEntry::STAGING; });
+            bool same = true;
+            if (e->state.load(std::memory_order_acquire) != FrameEntry::FAILED) same = rows_match_snapshot(e, l, r, ya, yb);
+            if (same) wait_for([&] { const int st = e->state.load(std::memory_order_acquire); return st == FrameEntry::READY || st == FrameEntry::FAILED; });
+            { std::lock_guard<SpinLock> g(c->cache_mu); state = e->state; rc = e->rc; if (!same) e->stale = true; }
+            if (!same) {
+                release_entry(c, e, 0);
+                c->region_stale.fetch_add(1, std::memory_order_relaxed);
+                continue;                                                              // recompute from the caller's current pixels
+            }
         }
         if (state == FrameEntry::FAILED) { release_entry(c, e, 0); return rc; }       // every chunk of the frame reports the error
-        const int ya = std::max(0, y0 - half), yb = std::min(h, y1 + half);
-        if (!producer && !rows_match_snapshot(e, l, r, ya, yb)) {
-            { std::lock_guard<std::mutex> g(c->cache_mu); e->stale = true; }
-            release_entry(c, e, 0);
-            c->region_stale.fetch_add(1, std::memory_order_relaxed);
-            continue;                                                                  // recompute from the caller's current pixels
-        }
         const Slot* s = e->slot;
         for (int y = y0; y < y1; ++y)                                                  // region-local rows: OutputChunk.DisparityData (sad.go:91)
             memcpy(out + (size_t)(y - y0) * out_stride, s->hOut + (size_t)y * s->pitch + x0, (size_t)(x1 - x0));

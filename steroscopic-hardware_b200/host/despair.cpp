@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <deque>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -99,14 +100,17 @@ void ShutdownBackend()
 
 Pipeline SetupConcurrentSAD(int numWorkers)
 {
-    if (numWorkers <= 0) numWorkers = (int)std::max(1u, std::thread::hardware_concurrency()) * 4;   // sad.go:32-34
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (numWorkers <= 0) numWorkers = hw * 4;                                                        // sad.go:32-34
     Pipeline p{std::make_shared<Chan<InputChunk>>((size_t)numWorkers * 2),
                std::make_shared<Chan<OutputChunk>>((size_t)numWorkers * 2)};                          // :36-37
-    auto live = std::make_shared<std::atomic<int>>(numWorkers);
-    for (int w = 0; w < numWorkers; ++w) {
-        std::thread([in = p.In, out = p.Out, live] {
-            InputChunk chunk;
-            while (in->Recv(chunk)) {                      // for chunk := range inputChan  (:47)
+    const int threads = std::max(1, std::min(numWorkers, hw / 2));           // OS threads that carry the logical workers
+    const int quota = (numWorkers + threads - 1) / threads;                  // chunks one thread may hold: threads * quota >= numWorkers
+    auto live = std::make_shared<std::atomic<int>>(threads);
+    for (int t = 0; t < threads; ++t) {
+        std::thread([in = p.In, out = p.Out, live, quota] {
+            std::deque<OutputChunk> held;                  // finished chunks the output channel had no room for yet
+            auto work = [&](const InputChunk& chunk) {     // the worker body, sad.go:47-102
                 Parameters params = DefaultParams();       // snapshot per chunk (:51-53)
                 OutputChunk result;
                 try {
@@ -116,8 +120,36 @@ Pipeline SetupConcurrentSAD(int numWorkers)
                     result = OutputChunk{};
                     result.Region = chunk.Region;
                 }
-                try { out->Send(std::move(result)); } catch (...) { break; }
-            }
+                held.push_back(std::move(result));
+            };
+            try {
+                for (bool open = true; open || !held.empty();) {
+                    bool progress = false;
+                    while (!held.empty() && out->TrySend(held.front())) { held.pop_front(); progress = true; }
+                    if (open && (int)held.size() < quota) {
+                        InputChunk chunk;
+                        // nothing held: sleep in the channel like `for chunk := range inputChan` (:47); otherwise only look
+                        const int got = held.empty() ? (in->Recv(chunk) ? 1 : -1) : in->TryRecv(chunk);
+                        if (got > 0) { work(chunk); progress = true; }
+                        else if (got < 0) open = false;
+                    }
+                    if (!progress && !held.empty()) {
+                        if (!open || (int)held.size() >= quota) { out->Send(std::move(held.front())); held.pop_front(); continue; }   // nothing else to do
+                        // room in the quota: wait for a place in the output OR a chunk in the input — poll both for a while, then doze
+                        const auto t0 = std::chrono::steady_clock::now();
+                        bool ready = false;
+                        while (!ready && std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(100)) {
+                            for (int i = 0; i < 64 && !ready; ++i) {
+                                ready = out->Size() < out->Cap() || in->Size() > 0;
+#if defined(__x86_64__) || defined(__i386__)
+                                if (!ready) __builtin_ia32_pause();
+#endif
+                            }
+                        }
+                        if (!ready) out->WaitNotFullFor(std::chrono::microseconds(50));
+                    }
+                }
+            } catch (...) {}                               // send on a closed output channel: the pipeline is being torn down
             if (live->fetch_sub(1) == 1) out->Close();     // wg.Wait(); close(outputChan)  (:107-110)
         }).detach();
     }

@@ -23,6 +23,9 @@
 // surfaces as std::runtime_error from AssembleDisparityMap / RunSad where Go would panic — never as a
 // silently black map.
 #pragma once
+#include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
@@ -31,6 +34,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 struct sadgpu_ctx;
@@ -75,42 +79,138 @@ struct OutputChunk {                    // sad.go:18-21
     Rectangle Region;
 };
 
-template <class T> class Chan {         // buffered Go channel
+// Buffered Go channel.  OutputCamera moves 160 chunks per frame through two of these (pkg/camera/output.go:176-190), so the
+// hot path must cost what a goroutine channel costs: the queue is a bounded lock-free ring (per-cell sequence numbers,
+// D. Vyukov's MPMC queue) — a contended std::mutex costs 1.6 us per operation on the GPU hosts, the ring 0.1 us — and
+// blocking is poll-then-sleep: receivers and senders poll for some tens of microseconds before they sleep (a goroutine parks
+// in ~100 ns, a futex sleep / wake pair costs ~10 us), at most half the cores poll at a time, and a wake-up system call is
+// only made when somebody is asleep and more items are queued than there are pollers to take them.
+// The ring holds the next power of two >= cap items (more buffering than Go's exact cap never blocks a correct program).
+template <class T> class Chan {
 public:
-    explicit Chan(size_t cap) : cap_(cap ? cap : 1) {}
-    void Send(T v) {
-        std::unique_lock<std::mutex> l(m_);
-        not_full_.wait(l, [&] { return q_.size() < cap_ || closed_; });
-        if (closed_) throw std::runtime_error("send on closed channel");
-        q_.push_back(std::move(v));
-        not_empty_.notify_one();
+    explicit Chan(size_t cap) : cap_(cap ? cap : 1) {
+        size_t n = 1;
+        while (n < cap_) n <<= 1;
+        mask_ = n - 1;
+        cells_.reset(new Cell[n]);
+        for (size_t i = 0; i < n; ++i) cells_[i].seq.store(i, std::memory_order_relaxed);
     }
-    bool Recv(T& out) {                 // false once the channel is closed and drained (Go: v, ok := <-ch)
-        std::unique_lock<std::mutex> l(m_);
-        not_empty_.wait(l, [&] { return !q_.empty() || closed_; });
-        if (q_.empty()) return false;
-        out = std::move(q_.front());
-        q_.pop_front();
-        not_full_.notify_one();
+    // Non-blocking forms (SetupConcurrentSAD runs several logical workers on one thread).
+    bool TrySend(T& v) {                // moves from v on success
+        if (closed_.load(std::memory_order_acquire)) throw std::runtime_error("send on closed channel");
+        size_t pos = enq_.load(std::memory_order_relaxed);
+        Cell* c;
+        for (;;) {
+            c = &cells_[pos & mask_];
+            const intptr_t dif = (intptr_t)c->seq.load(std::memory_order_acquire) - (intptr_t)pos;
+            if (dif == 0) { if (enq_.compare_exchange_weak(pos, pos + 1, std::memory_order_relaxed)) break; }
+            else if (dif < 0) return false;                                    // full
+            else pos = enq_.load(std::memory_order_relaxed);
+        }
+        c->data = std::move(v);
+        c->seq.store(pos + 1, std::memory_order_release);
+        if (recv_sleepers_.load(std::memory_order_seq_cst) > 0 && (int)Size() > spinners_.load(std::memory_order_relaxed)) {
+            std::lock_guard<std::mutex> l(sm_);
+            not_empty_.notify_one();
+        }
         return true;
     }
+    int TryRecv(T& out) {               // 1 = received, 0 = empty, -1 = closed and drained
+        for (int attempt = 0;; ++attempt) {
+            size_t pos = deq_.load(std::memory_order_relaxed);
+            Cell* c;
+            bool got = false;
+            for (;;) {
+                c = &cells_[pos & mask_];
+                const intptr_t dif = (intptr_t)c->seq.load(std::memory_order_acquire) - (intptr_t)(pos + 1);
+                if (dif == 0) { if (deq_.compare_exchange_weak(pos, pos + 1, std::memory_order_relaxed)) { got = true; break; } }
+                else if (dif < 0) break;                                       // empty
+                else pos = deq_.load(std::memory_order_relaxed);
+            }
+            if (got) {
+                out = std::move(c->data);
+                c->seq.store(pos + mask_ + 1, std::memory_order_release);
+                // hysteresis: one wake-up for many free places, not one per place (senders never sleep without a time limit)
+                if (send_sleepers_.load(std::memory_order_seq_cst) > 0 && Size() <= (mask_ + 1) / 2) {
+                    std::lock_guard<std::mutex> l(sm_);
+                    not_full_.notify_all();
+                }
+                return 1;
+            }
+            if (!closed_.load(std::memory_order_acquire)) return 0;
+            if (attempt) return -1;                                            // closed: one more look for an item sent before Close
+        }
+    }
+    void Send(T v) {
+        for (;;) {
+            if (TrySend(v)) return;
+            if (spin_until([&] { return Size() <= mask_ || closed_.load(std::memory_order_relaxed); })) continue;
+            std::unique_lock<std::mutex> l(sm_);
+            send_sleepers_.fetch_add(1, std::memory_order_seq_cst);
+            if (Size() > mask_ && !closed_.load(std::memory_order_relaxed)) not_full_.wait_for(l, std::chrono::microseconds(100));
+            send_sleepers_.fetch_sub(1, std::memory_order_seq_cst);
+        }
+    }
+    bool Recv(T& out) {                 // false once the channel is closed and drained (Go: v, ok := <-ch)
+        for (;;) {
+            const int r = TryRecv(out);
+            if (r) return r > 0;
+            if (spin_until([&] { return Size() > 0 || closed_.load(std::memory_order_relaxed); })) continue;
+            std::unique_lock<std::mutex> l(sm_);
+            recv_sleepers_.fetch_add(1, std::memory_order_seq_cst);
+            if (Size() == 0 && !closed_.load(std::memory_order_relaxed)) not_empty_.wait_for(l, std::chrono::milliseconds(2));
+            recv_sleepers_.fetch_sub(1, std::memory_order_seq_cst);
+        }
+    }
+    void WaitNotFullFor(std::chrono::microseconds d) {
+        std::unique_lock<std::mutex> l(sm_);
+        send_sleepers_.fetch_add(1, std::memory_order_seq_cst);
+        if (Size() > mask_ && !closed_.load(std::memory_order_relaxed)) not_full_.wait_for(l, d);
+        send_sleepers_.fetch_sub(1, std::memory_order_seq_cst);
+    }
     void Close() {
-        std::lock_guard<std::mutex> l(m_);
-        closed_ = true;
+        closed_.store(true, std::memory_order_release);
+        std::lock_guard<std::mutex> l(sm_);
         not_empty_.notify_all();
         not_full_.notify_all();
     }
-    size_t Cap() const { return cap_; }
+    size_t Cap() const { return mask_ + 1; }
+    size_t Size() const {               // a glance (pollers): exact when nobody is in the middle of an operation
+        const size_t e = enq_.load(std::memory_order_relaxed), d = deq_.load(std::memory_order_relaxed);
+        return e > d ? e - d : 0;
+    }
     // Error side band (the Go structs have no error field): the first backend failure of a worker is recorded on the output
     // channel; AssembleDisparityMap reports it instead of returning a map with holes.
-    void Fail(const std::string& what) { std::lock_guard<std::mutex> l(m_); if (err_.empty()) err_ = what; }
-    std::string TakeError() { std::lock_guard<std::mutex> l(m_); std::string e; e.swap(err_); return e; }
+    void Fail(const std::string& what) { std::lock_guard<std::mutex> l(sm_); if (err_.empty()) err_ = what; }
+    std::string TakeError() { std::lock_guard<std::mutex> l(sm_); std::string e; e.swap(err_); return e; }
 private:
-    std::mutex m_;
+    struct Cell { std::atomic<size_t> seq; T data; };
+    template <class Pred> bool spin_until(Pred ready) {              // true: the condition held before the spin budget ran out
+        if (ready()) return true;
+        static const int limit = std::max(1, (int)std::thread::hardware_concurrency() / 2 + 1);
+        if (spinners_.fetch_add(1, std::memory_order_relaxed) >= limit) { spinners_.fetch_sub(1, std::memory_order_relaxed); return ready(); }
+        const auto t0 = std::chrono::steady_clock::now();
+        bool ok = false;
+        for (;;) {
+            for (int i = 0; i < 64 && !ok; ++i) {
+                ok = ready();
+#if defined(__x86_64__) || defined(__i386__)
+                if (!ok) __builtin_ia32_pause();
+#endif
+            }
+            if (ok || std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(50)) break;
+        }
+        spinners_.fetch_sub(1, std::memory_order_relaxed);
+        return ok || ready();
+    }
+    size_t cap_, mask_ = 0;
+    std::unique_ptr<Cell[]> cells_;
+    alignas(64) std::atomic<size_t> enq_{0};
+    alignas(64) std::atomic<size_t> deq_{0};
+    alignas(64) std::atomic<bool> closed_{false};
+    std::atomic<int> spinners_{0}, recv_sleepers_{0}, send_sleepers_{0};
+    std::mutex sm_;                      // sleepers only
     std::condition_variable not_empty_, not_full_;
-    std::deque<T> q_;
-    size_t cap_;
-    bool closed_ = false;
     std::string err_;
 };
 
@@ -120,6 +220,10 @@ struct Pipeline {                       // the (chan<- InputChunk, <-chan Output
 };
 
 // numWorkers <= 0 => hardware_concurrency*4 (sad.go:32-34); channels buffered 2*numWorkers (:36-37).
+// Go runs its numWorkers goroutines on GOMAXPROCS threads; here the numWorkers logical workers run on at most half the
+// cores' worth of threads, each of which may hold several finished chunks, so that the pipeline keeps the reference's capacity
+// of 2n + n + 2n chunks in flight (OutputCamera sends all 160 chunks of a frame before it starts receiving,
+// pkg/camera/output.go:176-190: with fewer than n chunks held by workers it would deadlock).
 Pipeline SetupConcurrentSAD(int numWorkers);
 Gray RunSad(const Gray& left, const Gray& right, int blockSize, int maxDisparity);
 Gray AssembleDisparityMap(Chan<OutputChunk>& outputChan, Rectangle dimensions, int chunks, bool faithful_drop = false);
