@@ -13,7 +13,13 @@ HBM).  Frame-sharded over ranks, no collective on the data path (SURVEY.md §8(e
                against the measured 64 lane-ops/clk/SM; HBM figures beside it
   cpu_baseline the oracle's literal restatement of pkg/despair on the host cores (rank 0, N=1)
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  extra        every other BASELINE.json config, measured and parity-checked in the same run: cfg1, cfg2 (intended luma and the
+               all-zero images LoadPNG really produces), cfg4 on one GPU and row-band sharded over all N GPUs
+               (sadgpu_compute_sharded), the cfg5 sweep (1024 pairs frame-sharded over the ranks x the full WebUI grid
+               B {3..31 odd, 16} x D {16..256 step 16}), and the UNCHANGED reference call pattern of OutputCamera
+               (SetupConcurrentSAD(32), H/128-row bands, pageable buffers) through the C++ mirror
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extra]
 """
 import argparse
 import json
@@ -50,6 +56,219 @@ def stream_frame(seed, h=H, w=W, ramp=56):
 
 def mpixd(frames, seconds):
     return W * H * D * frames / seconds / 1e6
+
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+UI_BLOCKS = list(range(3, 32, 2)) + [16]          # cmd/components/control.templ:25-27 + the start-up default (params.go:13-18)
+UI_DISPARITIES = list(range(16, 257, 16))         # control.templ:71-73
+CFG5_PAIRS = 1024                                 # BASELINE.json configs[4]
+
+
+def p_int_peak():
+    try:
+        ip = json.load(open(os.path.join(ROOT, "profiles", "r01_int_peaks.json")))
+        return (ip["iadd3"]["lane_ops_per_clk_per_sm"] * ip["sms"] * ip["clock_rate_khz"] * 1e3 / 1e12,
+                "profiles/r01_int_peaks.json: measured 63.9 IADD3 lane-ops/clk/SM x 148 SMs x 1.965 GHz")
+    except Exception:
+        return 148 * 64 * 1.965e9 / 1e12, "theoretical 148 SM x 64 lanes x 1.965 GHz"
+
+
+def frac_of_roofline(w, h, d, us_per_frame, n_gpus=1):
+    return OPS_PER_EVAL * w * h * (d + 1) / (us_per_frame * 1e-6) / 1e12 / (p_int_peak()[0] * n_gpus)
+
+
+def time_device_batch(torch, ctx, dL, dR, dO, w, h, b, d, fb, reps, warm=1):
+    """CUDA-event time of `reps` passes over the resident frame set (launches of fb frames), microseconds per frame."""
+    st = torch.cuda.current_stream()
+    n = dL.shape[0]
+
+    def one_pass():
+        for k in range(0, n, fb):
+            m = min(fb, n - k)
+            ctx.compute_device_batch(m, dL[k].data_ptr(), w, w * h, dR[k].data_ptr(), w, w * h, w, h, b, d,
+                                     dO[k].data_ptr(), w, w * h, cuda_stream=st.cuda_stream)
+    for _ in range(warm):
+        one_pass()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for _ in range(reps):
+        one_pass()
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (reps * n)
+
+
+def load_gray(name):
+    from PIL import Image
+    return np.array(Image.open(os.path.join(GOLDEN, name)), np.uint8)
+
+
+def sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def extra_single_gpu_configs(torch, despair, O, device_index):
+    """cfg1, cfg2 and cfg4 on ONE GPU, device-resident, inputs larger than L2 per pass; parity against the committed golden
+    fixtures (SURVEY.md §8(c) SHA pins) and the oracle."""
+    out = {}
+    man = json.load(open(os.path.join(GOLDEN, "manifest.json")))
+    ctx = despair.Context([device_index], 3840, 2160, 1)
+    try:
+        # cfg1: the four testdata pairs (Go-exact gray), block 9, max disparity 64; 1280 frames = 786 MB of input per pass
+        tags = list(man["pairs"].keys())
+        Ls = [load_gray(f"L_{t}_gray.png") for t in tags]; Rs = [load_gray(f"R_{t}_gray.png") for t in tags]
+        n = 1280
+        dL = torch.stack([torch.from_numpy(Ls[k % len(tags)]) for k in range(n)]).cuda()
+        dR = torch.stack([torch.from_numpy(Rs[k % len(tags)]) for k in range(n)]).cuda()
+        dO = torch.zeros_like(dL)
+        us = time_device_batch(torch, ctx, dL, dR, dO, 640, 480, 9, 64, 64, 3)
+        got = dO[:len(tags)].cpu().numpy()
+        ok = all(sha(got[i]) == man["pairs"][t]["b9_d64_sha256"] for i, t in enumerate(tags))
+        out["cfg1"] = {"workload": "testdata L/R_00001,00002,00335,01000 (640x480), block 9, max disparity 64", "us_per_frame": us,
+                       "frames_per_sec": 1e6 / us, "frac": frac_of_roofline(640, 480, 64, us), "frames_per_launch": 64,
+                       "parity": bool(ok), "parity_against": "SHA-256 pins of SURVEY.md §8(c) (tests/golden/manifest.json), all four pairs",
+                       "plan": despair.plan_describe(640, 480, 9, 64, frames=64)}
+        del dL, dR, dO
+        # cfg2: im0/im1 at 1920x1080, block 15, max disparity 256: intended luma, and the all-zero images LoadPNG really yields
+        L = load_gray("im0_intended_gray.png"); R = load_gray("im1_intended_gray.png")
+        n = 64
+        dL = torch.from_numpy(L).cuda().unsqueeze(0).repeat(n, 1, 1).contiguous(); dR = torch.from_numpy(R).cuda().unsqueeze(0).repeat(n, 1, 1).contiguous()
+        dO = torch.zeros_like(dL)
+        us = time_device_batch(torch, ctx, dL, dR, dO, 1920, 1080, 15, 256, 16, 2)
+        ok = sha(dO[n - 1].cpu().numpy()) == man["survey_pins"]["im0_im1_intended_b15_d256"]
+        dL.zero_(); dR.zero_()
+        us0 = time_device_batch(torch, ctx, dL, dR, dO, 1920, 1080, 15, 256, 16, 2)
+        ok0 = sha(dO[0].cpu().numpy()) == man["survey_pins"]["zeros_1920x1080"]
+        out["cfg2"] = {"workload": "im0/im1 1920x1080, block 15, max disparity 256", "us_per_frame": us, "frames_per_sec": 1e6 / us,
+                       "frac": frac_of_roofline(1920, 1080, 256, us), "frames_per_launch": 16, "parity": bool(ok),
+                       "parity_against": "SHA-256 pin of the intended-luma map (SURVEY.md §8(c))",
+                       "faithful_zero_images": {"us_per_frame": us0, "parity": bool(ok0),
+                                                "note": "LoadPNG as written turns 8-bit RGB files into all-zero images (gray.go:35-37): the map is all zero"},
+                       "plan": despair.plan_describe(1920, 1080, 15, 256, frames=16)}
+        del dL, dR, dO
+        # cfg4 on one GPU: 3840x2160, block 31, max disparity 256; 16 frames = 265 MB of input per pass
+        L, R = stream_frame(4321, 2160, 3840, 240)
+        n = 16
+        dL = torch.from_numpy(L).cuda().unsqueeze(0).repeat(n, 1, 1).contiguous(); dR = torch.from_numpy(R).cuda().unsqueeze(0).repeat(n, 1, 1).contiguous()
+        dO = torch.zeros_like(dL)
+        us = time_device_batch(torch, ctx, dL, dR, dO, 3840, 2160, 31, 256, 2, 2)
+        rows = dO[n - 1, 1000:1016].cpu().numpy()
+        ok = np.array_equal(rows, O.frame_box(L, R, 31, 256, 1000, 1016))
+        out["cfg4_one_gpu"] = {"workload": "synthetic 3840x2160, block 31, max disparity 256, device-resident", "us_per_frame": us,
+                               "frames_per_sec": 1e6 / us, "frac": frac_of_roofline(3840, 2160, 256, us), "frames_per_launch": 2,
+                               "parity": bool(ok), "parity_against": "oracle rows 1000..1015",
+                               "plan": despair.plan_describe(3840, 2160, 31, 256, frames=2)}
+        del dL, dR, dO
+        torch.cuda.empty_cache()
+    finally:
+        ctx.close()
+    return out
+
+
+def extra_cfg4_sharded(despair, O, n_devices):
+    """cfg4 as BASELINE.json names it: ONE 3840x2160 pair, block 31, max disparity 256, row bands + 15-row halo over n_devices GPUs
+    of one process (sadgpu_compute_sharded), host buffers in, host-side gather out.  Latency of one frame, pinned and pageable."""
+    L, R = stream_frame(4321, 2160, 3840, 240)
+    ctx = despair.Context(list(range(n_devices)), 3840, 2160, max(n_devices, 4 if n_devices == 1 else n_devices))
+    try:
+        pl, pr = ctx.host_pair(2160, 3840); pl[:] = L; pr[:] = R
+        po = ctx.host_array((2160, 3840))
+        res = {}
+        for name, (a, b, o) in (("pinned", (pl, pr, po)), ("pageable", (L, R, np.zeros((2160, 3840), np.uint8)))):
+            for _ in range(2):
+                ctx.compute_sharded(a, b, 31, 256, out=o)
+            t0 = time.perf_counter(); reps = 8
+            for _ in range(reps):
+                ctx.compute_sharded(a, b, 31, 256, out=o)
+            res[name] = (time.perf_counter() - t0) / reps
+            if name == "pinned":
+                ok = np.array_equal(o[1000:1016], O.frame_box(L, R, 31, 256, 1000, 1016)) and \
+                    np.array_equal(o[2150:2160], O.frame_box(L, R, 31, 256, 2150, 2160))
+        return {"workload": "ONE synthetic 3840x2160 pair per call, block 31, max disparity 256, row bands + 15-row halo, host buffers",
+                "n_gpus": n_devices, "ms_per_frame_pinned": res["pinned"] * 1e3, "ms_per_frame_pageable": res["pageable"] * 1e3,
+                "frames_per_sec": 1 / res["pinned"], "Mpix_D_per_s": 3840 * 2160 * 256 / res["pinned"] / 1e6, "parity": bool(ok),
+                "parity_against": "oracle rows 1000..1015 and 2150..2159 (band borders included)", "collective": "none (host-side gather)"}
+    finally:
+        ctx.close()
+
+
+def extra_cfg5_sweep(torch, dist, despair, O, ctx, rank, world, gen):
+    """cfg5: 1024 frame pairs of the cfg3 generator, frame-sharded over the ranks (frame k -> rank k mod world), the full WebUI
+    grid.  Every rank times its own share per point with CUDA events; the job time of a point is the max over ranks."""
+    per_rank = CFG5_PAIRS // world
+    nuniq = len(gen)
+    dL = torch.empty((per_rank, H, W), dtype=torch.uint8, device="cuda"); dR = torch.empty_like(dL)
+    for k in range(per_rank):
+        dL[k].copy_(torch.from_numpy(gen[k % nuniq][0])); dR[k].copy_(torch.from_numpy(gen[k % nuniq][1]))
+    dO = torch.zeros_like(dL)
+    points = [(b, d) for b in UI_BLOCKS for d in UI_DISPARITIES]
+    times = torch.zeros(len(points), dtype=torch.float64, device="cuda")
+    parity = []
+    for i, (b, d) in enumerate(points):
+        us = time_device_batch(torch, ctx, dL, dR, dO, W, H, b, d, 16, 1, warm=0 if per_rank >= 64 else 1)
+        times[i] = us * per_rank                              # microseconds this rank needed for its share
+        if rank == 0:
+            parity.append(bool(np.array_equal(dO[per_rank - 1, 520:528].cpu().numpy(),
+                                              O.frame_box(gen[(per_rank - 1) % nuniq][0], gen[(per_rank - 1) % nuniq][1], b, d, 520, 528))))
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    del dL, dR, dO
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    t = times.cpu().numpy()
+    pts = []
+    for i, (b, d) in enumerate(points):
+        us_job = float(t[i])
+        pts.append({"B": b, "D": d, "frames_per_sec": CFG5_PAIRS / (us_job * 1e-6), "us_per_frame_per_gpu": us_job / per_rank,
+                    "frac": frac_of_roofline(W, H, d, us_job / per_rank), "parity": parity[i],
+                    "variant": despair.plan_describe(W, H, b, d, frames=16)["variant"]})
+    fr = [p["frac"] for p in pts]
+    return {"workload": f"{CFG5_PAIRS} synthetic 1080p pairs (cfg3 generator) frame-sharded over {world} GPU(s), {len(points)} points: "
+                        f"block {{3..31 odd, 16}} x max disparity {{16..256 step 16}}", "frames_per_launch": 16,
+            "points": pts, "all_parity": bool(all(parity)), "parity_against": "oracle rows 520..527 of the last frame of rank 0's share",
+            "frac_min": min(fr), "frac_median": float(np.median(fr)), "frac_max": max(fr),
+            "sweep_seconds": float(t.sum() * 1e-6)}
+
+
+def extra_output_camera_path(despair, O):
+    """The UNCHANGED reference call pattern (pkg/camera/output.go:129-210 minus the PNG files) through the C++ mirror of pkg/despair:
+    SetupConcurrentSAD(32), every frame fresh pageable image objects, H/128-row bands, AssembleDisparityMap; against ONE synchronous
+    sadgpu_compute call of the same pageable frame."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "steroscopic-hardware_b200", "libdespair_host.so"))
+    u8p = ctypes.c_void_p
+    lib.despair_host_output_camera_loop.argtypes = [u8p, u8p] + [ctypes.c_int] * 9 + [u8p, ctypes.POINTER(ctypes.c_double)]
+    rng = np.random.default_rng(7)
+    legs = []
+    ctx = despair.Context([0], 1920, 1080, 1)
+    try:
+        for (w, h) in ((640, 480), (1920, 1080)):
+            b, d, n, warm, iters = 16, 64, 4, 5, 40           # the reference's start-up parameters (params.go:13-18)
+            base = rng.integers(0, 256, (n, h, w + 64), dtype=np.uint8)
+            L = np.ascontiguousarray(base[:, :, 64:]); R = np.ascontiguousarray(np.roll(base, -19, 2)[:, :, 64:])
+            o = np.zeros((h, w), np.uint8)
+            for _ in range(5):
+                ctx.compute(L[0], R[0], b, d, out=o)
+            t0 = time.perf_counter(); reps = 40
+            for k in range(reps):
+                ctx.compute(L[k % n], R[k % n], b, d, out=o)
+            one_call = (time.perf_counter() - t0) / reps * 1e6
+            us = ctypes.c_double(); last = np.zeros((h, w), np.uint8)
+            rc = lib.despair_host_output_camera_loop(L.ctypes.data, R.ctypes.data, n, w, h, b, d, 32, warm, iters, 0, last.ctypes.data, ctypes.byref(us))
+            k = (warm + iters - 1) % n
+            legs.append({"w": w, "h": h, "block_size": b, "max_disparity": d, "workers": 32, "chunks_per_frame": -(-h // max(1, h // 128)),
+                         "us_per_frame": us.value, "frames_per_sec": 1e6 / us.value if us.value else None,
+                         "one_sadgpu_compute_call_pageable_us": one_call, "ratio_to_one_call": us.value / one_call,
+                         "parity": bool(rc == 0 and np.array_equal(last, O.frame_box(L[k], R[k], b, d)))})
+        lib.despair_host_shutdown()
+    finally:
+        ctx.close()
+    return {"how": "despair::SetupConcurrentSAD(32) + row bands of H/128 rows + AssembleDisparityMap (C++ mirror, host/despair.cpp); each chunk is one "
+                   "sadgpu_compute_region call, the chunks of a frame share one GPU pass; buffers are pageable std::vector planes",
+            "legs": legs}
 
 
 class ClockSampler:
@@ -163,6 +382,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the legs for the other BASELINE configs (headline only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -176,7 +396,10 @@ def main():
         # The reference's own CPU implementation of the path (oracle port: Go toolchain absent), all host threads.
         if rank != 0:
             return
-        rows = 270                                     # bounded sample: a quarter frame per step
+        # bounded sample: about a quarter frame per step, a whole number of rounds of the thread pool over the production bands
+        # (H/128 = 8 rows each, output.go:172) so that no thread idles in the last round
+        band = max(1, H // 128)
+        rows = min(H, cores * band * max(1, round(270 / (cores * band))))
         v, sec, _ = cpu_reference_run(rows, cores, max(1, args.steps), min(args.warmup, 1))
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -318,6 +541,39 @@ def main():
         e2e_parity = bool(np.array_equal(outs[(nbatch - 1) % n_streams][EB - 1][520:536],
                                          O.frame_box(gen[fl][0], gen[fl][1], B, D, 520, 536)))
 
+    # ---- e2e from PAGEABLE caller memory: the synchronous drop-in call sadgpu_compute on plain numpy planes (what a Go Pix slice
+    #      is), one frame per call, the staging copies inside the call (rank 0's GPU only) ----
+    pageable = None
+    if rank == 0:
+        po = np.zeros((H, W), np.uint8)
+        for k in range(3):
+            ctx.compute(gen[k][0], gen[k][1], B, D, out=po)
+        t0 = time.perf_counter(); reps = 40
+        for k in range(reps):
+            ctx.compute(gen[k % nuniq][0], gen[k % nuniq][1], B, D, out=po)
+        dtp = (time.perf_counter() - t0) / reps
+        pageable = {"value": mpixd(1, dtp), "unit": UNIT, "frames_per_sec": 1 / dtp, "us_per_call": dtp * 1e6, "n_gpus": 1,
+                    "parity": bool(np.array_equal(po[520:536], O.frame_box(gen[(reps - 1) % nuniq][0], gen[(reps - 1) % nuniq][1], B, D, 520, 536))),
+                    "how": "sadgpu_compute, one 1080p pair per call from pageable numpy planes into a pageable map (staging inside the call)"}
+
+    # ---- the other BASELINE configs ----
+    extra = None
+    if not args.no_extra:
+        del dL, dR, dO
+        torch.cuda.empty_cache()
+        extra = {}
+        if rank == 0:
+            extra.update(extra_single_gpu_configs(torch, despair, O, local_rank))
+            extra["output_camera_path"] = extra_output_camera_path(despair, O)
+        barrier()
+        sweep = extra_cfg5_sweep(torch, dist, despair, O if rank == 0 else None, ctx, rank, world, gen)
+        barrier()
+        if rank == 0:
+            extra["cfg5_sweep"] = sweep
+            # cfg4 row-band sharded over ALL the GPUs of the job from one process (the other ranks idle at the barrier below)
+            extra["cfg4_row_bands"] = extra_cfg4_sharded(despair, O, world)
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -330,12 +586,7 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    try:
-        ip = json.load(open(os.path.join(ROOT, "profiles", "r01_int_peaks.json")))
-        p_int = ip["iadd3"]["lane_ops_per_clk_per_sm"] * ip["sms"] * ip["clock_rate_khz"] * 1e3 / 1e12
-        p_src = "profiles/r01_int_peaks.json: measured 63.9 IADD3 lane-ops/clk/SM x 148 SMs x 1.965 GHz"
-    except Exception:
-        p_int, p_src = 148 * 64 * 1.965e9 / 1e12, "theoretical 148 SM x 64 lanes x 1.965 GHz"
+    p_int, p_src = p_int_peak()
     us_per_frame = ms_max * 1e3 / (args.steps * F)
     us_per_launch = us_per_frame * FB
     evals = W * H * (D + 1) * FB                   # evaluations one launch processes
@@ -356,7 +607,8 @@ def main():
 
     cpu_baseline = None
     if args.gpus == 1 and not args.no_cpu_baseline:
-        rows = 540                                     # half a frame: ~10-30 core-seconds of literal SAD
+        band = max(1, H // 128)                        # half a frame, a whole number of rounds of the thread pool (see the reference arm)
+        rows = min(H, cores * band * max(1, round(540 / (cores * band))))
         v, sec, out = cpu_reference_run(rows, cores, 1, 0)
         ok = bool(np.array_equal(out, ctx.compute(*stream_frame(1234), B, D)[(H - rows) // 2:(H - rows) // 2 + rows]))
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -375,11 +627,12 @@ def main():
                            f"pinned host buffers both ways, {n_streams} streams in flight",
                     "single_frame_calls": {"value": mpixd(e2e_steps * F * world, dt_single), "unit": UNIT,
                                            "frames_per_sec": e2e_steps * F * world / dt_single,
-                                           "how": "sadgpu_submit_into/sadgpu_wait, one frame pair per call"}},
+                                           "how": "sadgpu_submit_into/sadgpu_wait, one frame pair per call"},
+                    "pageable": pageable},
             "gpu_launches": args.steps * batches_per_step * launches_per_batch, "frames_per_launch": FB,
             "host": {"cores": cores, "rank0_cpu_affinity": (f"{affinity[0]}-{affinity[-1]} ({len(affinity)} cpus, GPU-local)" if affinity else "unpinned")},
             "parity": parity, "plan": despair.plan_describe(W, H, B, D, frames=FB), "clocks": clocks,
-            "roofline": roofline, "cpu_baseline": cpu_baseline}
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "extra": extra}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
