@@ -182,8 +182,10 @@ const FastEntry kFast[8][3] = {
     {fast_entry<7, 9>(), fast_entry<7, 18>(), kNoEntry}};
 
 // warp-specialised kernel (sad_ws.cuh): h <= 4; mode 0..3 = chunks of 33 / 17 / 9 / 5 groups on 1 / 2 / 3 / 6 strips per CTA
+// h = 5..8: mode 1 only (17 groups on one strip, two rows per walker warp)
 #define WS_ROW(H) {ws_entry<H, 0>(), ws_entry<H, 1>(), ws_entry<H, 2>(), ws_entry<H, 3>()}
-const FastEntry kWs[5][4] = {WS_ROW(0), WS_ROW(1), WS_ROW(2), WS_ROW(3), WS_ROW(4)};
+#define WS_ROW17(H) {kNoEntry, ws_entry<H, 1>(), kNoEntry, kNoEntry}
+const FastEntry kWs[9][4] = {WS_ROW(0), WS_ROW(1), WS_ROW(2), WS_ROW(3), WS_ROW(4), WS_ROW17(5), WS_ROW17(6), WS_ROW17(7), WS_ROW17(8)};
 
 // large-window phase-alternating kernel (sad_wide.cuh): h = 8..15, chunks of 8 groups
 const FastEntry kWide[8] = {wide_entry<8>(), wide_entry<9>(), wide_entry<10>(), wide_entry<11>(), wide_entry<12>(), wide_entry<13>(),
@@ -222,7 +224,7 @@ bool vh_supported(int) { return false; }
 bool ring_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
 bool fast_supported(int B) { return B / 2 <= 7; }
 bool wide_supported(int B) { return B / 2 >= 8 && B / 2 <= 15; }
-bool ws_supported(int B) { return B / 2 <= 4; }
+bool ws_supported(int B) { return B / 2 <= 8; }
 
 // Planner default for block_size >= 10, from the measured variant sweep (profiles/r01_variant_sweep.json, inputs streaming
 // from HBM): a ring pass over 33 groups costs about 1.7x a pass of the phase-alternating kernel over 18 groups, a ring pass
@@ -246,7 +248,12 @@ int choose_kernel(int B, int D, const sadgpu_tuning* t, int* variant_out, int* m
     const int gpc = t ? t->groups_per_chunk : 0;               // tests: force smaller chunks
     if (variant < 0 || variant > 6) return SADGPU_EINVAL;
     if (variant == V_AUTO) {
-        if (ws_supported(B)) variant = V_WS;
+        // measured (profiles/r02_*): the warp-specialised kernel wins for every block_size <= 17 except where another kernel
+        // covers the whole range in ONE pass that two 17-group chunks cannot beat: 18 groups (max_disparity 65..68) at block_size
+        // 11..15 (phase-alternating kernel, 18-group instance) and <= 8 groups (max_disparity <= 28) at block_size 16, 17
+        if (half <= 4) variant = V_WS;
+        else if (half <= 7 && ng != 18) variant = V_WS;
+        else if (half == 8 && ng >= 9) variant = V_WS;
         else if (ring_auto(B, D)) variant = V_RING;
         else variant = fast_supported(B) ? V_FAST : V_WIDE;
     }
@@ -257,6 +264,7 @@ int choose_kernel(int B, int D, const sadgpu_tuning* t, int* variant_out, int* m
         if (!ws_supported(B)) return SADGPU_EINVAL;
         mode = ws_mode_for(ng);
         if (gpc > 0) { const int forced = gpc >= 33 ? 0 : gpc >= 17 ? 1 : gpc >= 9 ? 2 : 3; mode = std::max(mode, forced); }
+        if (half >= 5) mode = 1;                               // block_size 11..17: chunks of 17 groups
         fe = &kWs[half][mode];
         break;
     case V_FAST: {

@@ -40,29 +40,35 @@ def test_version_and_strerror(native):
 def test_plans_cover_the_parameter_surface(native):
     import despair
     for B in range(1, 32):
-        for D in (1, 16, 32, 64, 128, 255, 256):
+        for D in (1, 16, 32, 64, 68, 128, 255, 256):
             p = despair.plan_describe(1920, 1080, B, D)
             assert p["half"] == B // 2 and p["smem"] <= 232448 and p["NC"] * p["NGc"] >= p["NG"]
             assert p["grid"][0] * p["TW"] >= 1920
             if p["variant"] == "wide":
                 assert 16 <= B <= 31
             elif p["variant"] == "ring":
-                assert 10 <= B <= 31 and p["TW"] == 32 and p["NGc"] == (33 if B <= 15 else 17)
+                assert 18 <= B <= 31 and p["TW"] == 32 and p["NGc"] == 17
             elif p["variant"] == "warp-specialised":
-                assert B <= 9 and (p["NGc"], p["TW"]) in ((33, 32), (17, 64), (9, 96), (5, 192))
-                assert p["NC"] == 1 or p["NGc"] == 33            # only the 33-group layout ever chunks the range
+                if B <= 9:
+                    assert (p["NGc"], p["TW"]) in ((33, 32), (17, 64), (9, 96), (5, 192))
+                    assert p["NC"] == 1 or p["NGc"] == 33            # only the 33-group layout ever chunks the range
+                else:
+                    assert B <= 17 and (p["NGc"], p["TW"]) == (17, 32) and p["RB"] == 2 * (B // 2) + 2
             else:
-                assert p["variant"] == "fast" and 10 <= B <= 15
+                assert p["variant"] == "fast" and 10 <= B <= 15 and p["NG"] == 18
     assert despair.plan_describe(1920, 1080, 9, 128)["variant"] == "warp-specialised"
     assert despair.plan_describe(640, 480, 9, 64)["NGc"] == 17                    # cfg1: two strips x 16 groups + tail
     assert despair.plan_describe(1920, 1080, 9, 16)["NGc"] == 5
-    assert despair.plan_describe(1920, 1080, 15, 256)["variant"] == "ring"
-    assert despair.plan_describe(1920, 1080, 15, 64)["variant"] == "fast"
+    assert despair.plan_describe(1920, 1080, 15, 256)["variant"] == "warp-specialised"     # cfg2: four chunks of 17 groups
+    assert despair.plan_describe(1920, 1080, 15, 68)["variant"] == "fast"
     assert despair.plan_describe(1920, 1080, 31, 256)["variant"] == "ring"
     assert despair.plan_describe(1920, 1080, 31, 16)["variant"] == "wide"
-    assert despair.plan_describe(1920, 1080, 16, 64)["variant"] == "ring"        # the reference's start-up parameters (params.go:13-18)
+    assert despair.plan_describe(1920, 1080, 16, 16)["variant"] == "wide"
+    assert despair.plan_describe(1920, 1080, 16, 64)["variant"] == "warp-specialised"     # the reference's start-up parameters (params.go:13-18)
     with pytest.raises(despair.SadGpuError):
         despair.plan_describe(1920, 1080, 31, 256, tuning=dict(kernel_variant=2))      # phase-alternating kernel needs block_size <= 15
+    with pytest.raises(despair.SadGpuError):
+        despair.plan_describe(1920, 1080, 19, 64, tuning=dict(kernel_variant=3))       # warp-specialised kernel needs block_size <= 17
     for gone in (1, 5):                                                               # removed kernels are rejected, not substituted
         with pytest.raises(despair.SadGpuError):
             despair.plan_describe(1920, 1080, 15, 64, tuning=dict(kernel_variant=gone))

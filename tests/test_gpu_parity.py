@@ -86,9 +86,9 @@ def test_tilings_do_not_change_pixels(torch_mod, ctx, oracle):
         W = int(rng.integers(20, 260)); H = int(rng.integers(10, 120))
         B = int(rng.integers(1, 32)); D = int(rng.choice([5, 16, 64, 128, 256]))
         L, R = synth_pair(rng, H, W, i % 5)
-        if B > 15:
+        if B > 17 or (B > 15 and i % 2 == 0):
             tun = dict(band_rows=int(rng.integers(1, 50)), kernel_variant=4)
-        elif B <= 9 and i % 2:          # warp-specialised kernel: forced chunk sizes 33 / 17 / 9 / 5 groups = every lane layout, chunked ranges
+        elif B <= 17 and i % 2:         # warp-specialised kernel: forced chunk sizes 33 / 17 / 9 / 5 groups = every lane layout, chunked ranges
             tun = dict(band_rows=int(rng.integers(1, 50)), groups_per_chunk=int(rng.choice([33, 17, 9, 5])), kernel_variant=3)
         else:
             tun = dict(band_rows=int(rng.integers(1, 50)), groups_per_chunk=int(rng.integers(1, 21)), kernel_variant=2)
@@ -104,17 +104,18 @@ def test_tilings_do_not_change_pixels(torch_mod, ctx, oracle):
 
 @pytest.mark.parametrize("variant", [2, 3, 4, 6])
 def test_every_kernel_variant_agrees_with_oracle(torch_mod, ctx, oracle, variant):
-    """variant 2 = phase-alternating register-ring kernel (B <= 15), 3 = warp-specialised double-buffered kernel (B <= 9, every D:
-    1 / 2 / 3 / 5 strips per CTA), 4 = large-window kernel (B 16..31), 6 = H-ring mbarrier-pipelined kernel (B 10..31)."""
+    """variant 2 = phase-alternating register-ring kernel (B <= 15), 3 = warp-specialised double-buffered kernel (B <= 17, every D:
+    1 / 2 / 3 / 6 strips per CTA at B <= 9, 17-group chunks with 16- and 32-bit sums at B 10..17), 4 = large-window kernel
+    (B 16..31), 6 = H-ring mbarrier-pipelined kernel (B 10..31)."""
     rng = np.random.default_rng(60 + variant)
-    for i in range(24):
+    for i in range(48 if variant == 3 else 24):
         W = int(rng.integers(20, 400)); H = int(rng.integers(10, 100))
         if variant == 4:
             B = int(rng.integers(16, 32)); D = int(rng.choice([7, 16, 33, 64, 128, 200, 256]))
         elif variant == 6:
             B = int(rng.integers(10, 32)); D = int(rng.choice([7, 16, 33, 64, 128, 200, 256]))
         elif variant == 3:
-            B = int(rng.integers(1, 10)); D = int(rng.choice([1, 7, 16, 17, 20, 32, 33, 36, 48, 64, 65, 68, 100, 128, 129, 200, 256]))
+            B = int(rng.integers(1, 18)); D = int(rng.choice([1, 7, 16, 17, 20, 32, 33, 36, 48, 64, 65, 68, 100, 128, 129, 200, 256]))
         else:
             B = int(rng.integers(1, 16)); D = int(rng.choice([7, 16, 33, 64, 128, 200, 256]))
         L, R = synth_pair(rng, H, W, i % 5)
@@ -432,6 +433,7 @@ def test_row_band_sharding_across_devices(torch_mod, oracle):
 
 
 @pytest.mark.parametrize("variant,B,D", [(2, 13, 64), (2, 9, 16), (3, 9, 128), (3, 5, 200), (3, 9, 64), (3, 7, 32), (3, 3, 16), (3, 8, 48),
+                                         (3, 11, 64), (3, 13, 128), (3, 15, 256), (3, 16, 64), (3, 17, 200), (3, 14, 16),
                                          (4, 31, 256), (4, 16, 33),
                                          (6, 15, 256), (6, 11, 128), (6, 13, 40), (6, 31, 256), (6, 16, 64), (6, 22, 100)])
 def test_unaligned_pitch_and_odd_widths(torch_mod, ctx, oracle, variant, B, D):
@@ -453,7 +455,8 @@ def test_tma_tile_loader_matches_plain_loader(torch_mod, ctx, oracle):
     rng = np.random.default_rng(33)
     st = torch.cuda.current_stream().cuda_stream
     for (W, H, B, D, F) in [(64, 20, 9, 128, 1), (128, 37, 9, 128, 2), (320, 50, 5, 200, 3), (96, 9, 1, 68, 1), (160, 33, 8, 256, 2), (48, 70, 9, 100, 1),
-                            (640, 48, 9, 64, 2), (208, 31, 7, 40, 1), (400, 25, 9, 32, 2), (112, 40, 5, 16, 3), (336, 19, 3, 8, 1)]:
+                            (640, 48, 9, 64, 2), (208, 31, 7, 40, 1), (400, 25, 9, 32, 2), (112, 40, 5, 16, 3), (336, 19, 3, 8, 1),
+                            (256, 60, 11, 64, 2), (160, 45, 15, 128, 1), (192, 50, 16, 64, 2), (96, 70, 17, 256, 1), (128, 33, 13, 20, 1)]:
         Ls = rng.integers(0, 256, (F, H, W), dtype=np.uint8); Rs = rng.integers(0, 256, (F, H, W), dtype=np.uint8)
         dL = torch.from_numpy(Ls).cuda(); dR = torch.from_numpy(Rs).cuda()
         for no_tma in (0, 1):
