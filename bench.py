@@ -197,11 +197,13 @@ def extra_cfg4_sharded(despair, O, n_devices):
 def extra_cfg5_sweep(torch, dist, despair, O, ctx, rank, world, gen):
     """cfg5: 1024 frame pairs of the cfg3 generator, frame-sharded over the ranks (frame k -> rank k mod world), the full WebUI
     grid.  Every rank times its own share per point with CUDA events; the job time of a point is the max over ranks."""
-    per_rank = CFG5_PAIRS // world
+    from despair.sharding import frames_for_rank
+    mine = list(frames_for_rank(CFG5_PAIRS, rank, world))       # frame k of the stream -> rank k mod world
+    per_rank = len(mine)
     nuniq = len(gen)
     dL = torch.empty((per_rank, H, W), dtype=torch.uint8, device="cuda"); dR = torch.empty_like(dL)
-    for k in range(per_rank):
-        dL[k].copy_(torch.from_numpy(gen[k % nuniq][0])); dR[k].copy_(torch.from_numpy(gen[k % nuniq][1]))
+    for i, k in enumerate(mine):
+        dL[i].copy_(torch.from_numpy(gen[k % nuniq][0])); dR[i].copy_(torch.from_numpy(gen[k % nuniq][1]))
     dO = torch.zeros_like(dL)
     points = [(b, d) for b in UI_BLOCKS for d in UI_DISPARITIES]
     times = torch.zeros(len(points), dtype=torch.float64, device="cuda")
@@ -210,8 +212,8 @@ def extra_cfg5_sweep(torch, dist, despair, O, ctx, rank, world, gen):
         us = time_device_batch(torch, ctx, dL, dR, dO, W, H, b, d, 16, 1, warm=0 if per_rank >= 64 else 1)
         times[i] = us * per_rank                              # microseconds this rank needed for its share
         if rank == 0:
-            parity.append(bool(np.array_equal(dO[per_rank - 1, 520:528].cpu().numpy(),
-                                              O.frame_box(gen[(per_rank - 1) % nuniq][0], gen[(per_rank - 1) % nuniq][1], b, d, 520, 528))))
+            kl = mine[-1] % nuniq
+            parity.append(bool(np.array_equal(dO[per_rank - 1, 520:528].cpu().numpy(), O.frame_box(gen[kl][0], gen[kl][1], b, d, 520, 528))))
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     del dL, dR, dO
@@ -222,8 +224,8 @@ def extra_cfg5_sweep(torch, dist, despair, O, ctx, rank, world, gen):
     pts = []
     for i, (b, d) in enumerate(points):
         us_job = float(t[i])
-        pts.append({"B": b, "D": d, "frames_per_sec": CFG5_PAIRS / (us_job * 1e-6), "us_per_frame_per_gpu": us_job / per_rank,
-                    "frac": frac_of_roofline(W, H, d, us_job / per_rank), "parity": parity[i],
+        pts.append({"B": b, "D": d, "frames_per_sec": CFG5_PAIRS / (us_job * 1e-6), "us_per_frame_per_gpu": us_job / (CFG5_PAIRS / world),
+                    "frac": frac_of_roofline(W, H, d, us_job / (CFG5_PAIRS / world)), "parity": parity[i],
                     "variant": despair.plan_describe(W, H, b, d, frames=16)["variant"]})
     fr = [p["frac"] for p in pts]
     return {"workload": f"{CFG5_PAIRS} synthetic 1080p pairs (cfg3 generator) frame-sharded over {world} GPU(s), {len(points)} points: "
@@ -557,21 +559,39 @@ def main():
                     "how": "sadgpu_compute, one 1080p pair per call from pageable numpy planes into a pageable map (staging inside the call)"}
 
     # ---- the other BASELINE configs ----
+    def wait_for_rank0(tag, work):
+        """Rank 0 runs `work`; the other ranks sleep on the rendezvous store (a CPU wait: an NCCL barrier would park a spinning
+        kernel on every GPU and a spinning thread on every rank's core while rank 0 measures)."""
+        barrier()
+        res = None
+        if world == 1:
+            return work()
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            try:
+                res = work()
+            finally:
+                store.set(tag, "done")
+        else:
+            store.wait([tag])
+        return res
+
     extra = None
     if not args.no_extra:
         del dL, dR, dO
         torch.cuda.empty_cache()
         extra = {}
+        r0 = wait_for_rank0("extra_single", lambda: {**extra_single_gpu_configs(torch, despair, O, local_rank),
+                                                     "output_camera_path": extra_output_camera_path(despair, O)})
         if rank == 0:
-            extra.update(extra_single_gpu_configs(torch, despair, O, local_rank))
-            extra["output_camera_path"] = extra_output_camera_path(despair, O)
+            extra.update(r0)
         barrier()
         sweep = extra_cfg5_sweep(torch, dist, despair, O if rank == 0 else None, ctx, rank, world, gen)
-        barrier()
+        # cfg4 row-band sharded over ALL the GPUs of the job from ONE process (rank 0); the other ranks' GPUs must be idle
+        bands = wait_for_rank0("extra_cfg4", lambda: extra_cfg4_sharded(despair, O, world))
         if rank == 0:
             extra["cfg5_sweep"] = sweep
-            # cfg4 row-band sharded over ALL the GPUs of the job from one process (the other ranks idle at the barrier below)
-            extra["cfg4_row_bands"] = extra_cfg4_sharded(despair, O, world)
+            extra["cfg4_row_bands"] = bands
         barrier()
 
     if rank != 0:
@@ -616,6 +636,18 @@ def main():
                                   f"(oracle, Go toolchain unavailable), H/128-row bands on {cores} pthreads",
                         "matches_gpu": ok}
 
+    # the copy-only ceiling of this class of box at N GPUs (tools/pcie_ngpu.py: the same transfers, no kernels)
+    ceiling = None
+    try:
+        pj = json.load(open(os.path.join(ROOT, "profiles", "r02_pcie_ngpu.json")))
+        for r in pj["runs"]:
+            if r["n_gpus"] == world and r["direction"] == "both" and r["driver"] == "one process per GPU":
+                ceiling = {"copy_only_frame_pairs_per_sec": r["frame_pairs_per_s"], "total_GBps": r["total_GBps"],
+                           "e2e_fraction_of_ceiling": (e2e_frames / dt_e2e) / r["frame_pairs_per_s"],
+                           "source": "profiles/r02_pcie_ngpu.json (8-pair H2D + 8-map D2H copies only, 4 in flight per GPU, one process per GPU)"}
+    except Exception:
+        pass
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload,
@@ -628,7 +660,7 @@ def main():
                     "single_frame_calls": {"value": mpixd(e2e_steps * F * world, dt_single), "unit": UNIT,
                                            "frames_per_sec": e2e_steps * F * world / dt_single,
                                            "how": "sadgpu_submit_into/sadgpu_wait, one frame pair per call"},
-                    "pageable": pageable},
+                    "pageable": pageable, "pcie_ceiling": ceiling},
             "gpu_launches": args.steps * batches_per_step * launches_per_batch, "frames_per_launch": FB,
             "host": {"cores": cores, "rank0_cpu_affinity": (f"{affinity[0]}-{affinity[-1]} ({len(affinity)} cpus, GPU-local)" if affinity else "unpinned")},
             "parity": parity, "plan": despair.plan_describe(W, H, B, D, frames=FB), "clocks": clocks,

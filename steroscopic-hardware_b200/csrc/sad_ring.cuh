@@ -54,6 +54,9 @@ template <int HALF> struct RingCfg {
     static constexpr int TW = 32, TWP = 33;
     static constexpr int NSTEP = TW + 2 * HALF;
     static constexpr int LW = (NSTEP + 3) & ~3;
+#ifndef RING_PAD
+#define RING_PAD 1
+#endif
     // h <= 7: chunks of 33 groups (walker lanes = 32 groups); h >= 8: the window needs up to 40 ring rows, so a chunk has 17
     // groups (walker lanes = 16 groups x 2 column halves) and a ring row is half as large
     static constexpr int NGC = WIDE ? 17 : 33, NGL = NGC - 1, GT = WIDE ? RING_WIDE_GT : 3, K = WIDE ? 18 / RING_WIDE_GT : 11;
@@ -81,14 +84,19 @@ template <int HALF> struct RingCfg {
     static constexpr int OFF = ((-(HALF + 3)) % 4 + 4) % 4;
     static constexpr int NWALKW = ((NSTEP - 1 + OFF) >> 2) + 2;
     static constexpr int RW = NGC - 1 + NWALKW;                     // words per aligned-R tile row
+    // tile row strides: with two rows per walker warp (17-group instances) the strides are padded to 4 / 12 mod 32 words so that the
+    // loads of different rows fall into different banks (the same padding took the warp-specialised kernel from 78 to 58 us at
+    // block 16, max disparity 64)
+    static constexpr int LWS = (WIDE && RING_PAD) ? LW + ((4 - LW % 32 + 32) % 32) : LW;
+    static constexpr int RWS = (WIDE && RING_PAD) ? RW + ((12 - RW % 32 + 32) % 32) : RW;
     static constexpr int HROW = (PKATOM ? NGC : NGS) * TWP;         // uint2 per H row
     static constexpr int NT = 768;
     // warp roles; SM sub-partition = warp % 4
     static constexpr int W_CONS = 8, W_TAIL = 19, W_FIN = 20, W_LD0 = 21, W_LD1 = 22, W_FIN2 = 23;
     static constexpr int H_BYTES = (NRH * HROW + (NGS - NGC) * TWP) * 8;    // + the surplus slot of the last row
     static constexpr int OFF_L = ((H_BYTES + 15) / 16) * 16;
-    static constexpr int OFF_R = OFF_L + TR * LW * 4;
-    static constexpr int OFF_PK = OFF_R + TR * RW * 4;              // [2][NWK][PKK][TW]
+    static constexpr int OFF_R = OFF_L + TR * LWS * 4;
+    static constexpr int OFF_PK = OFF_R + TR * RWS * 4;             // [2][NWK][PKK][TW]
     static constexpr int OFF_LUT = OFF_PK + 2 * NWK * PKK * TW * 4;
     static constexpr int OFF_BAR = ((OFF_LUT + 1040 + 7) / 8) * 8;
     static constexpr int WSPLIT = WMODE == 2 ? 1 : 2;               // column segments of a row walk
@@ -213,8 +221,8 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
         for (int bi = 0; bi < nbur; ++bi) {
             const int r = NWK * bi + wr, bs = bi % NB;
             const int ts = r % TR;
-            const uint32_t* Lr = Lrep + ts * LW + HW * wh;
-            const uint32_t* Rr = Ral + ts * RW + (NGC - 1 - gl) + (HW / 4) * wh;
+            const uint32_t* Lr = Lrep + ts * C::LWS + HW * wh;
+            const uint32_t* Rr = Ral + ts * C::RWS + (NGC - 1 - gl) + (HW / 4) * wh;
             uint2* Hout = Hs + (bs * NWK + wr) * HROW + gl * TWP + HW * wh;
             if (C::WMODE != 2) {                               // one row per warp: everything below is warp-uniform
                 if (r < nin) {
@@ -255,8 +263,8 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                 }
                 if (!C::ROWREL && pass == 0 && bi >= NB) RING_WAIT(hempty + 8 * bs, (uint32_t)(bi / NB - 1) & 1u, 1);
                 __syncwarp();
-                const uint32_t* Lr = Lrep + ts * LW + C::SEGW * s;
-                const uint32_t* Rr = Ral + ts * RW + (C::SEGW / 4) * s;
+                const uint32_t* Lr = Lrep + ts * C::LWS + C::SEGW * s;
+                const uint32_t* Rr = Ral + ts * C::RWS + (C::SEGW / 4) * s;
                 uint2* Hout = Hs + (bs * NWK + ((C::TPASS == 1 || j < NWK) ? j : 0)) * HROW + (NGC - 1) * TWP + C::SEGW * s;
                 if (nvalid >= C::NSTEP) sad_walk<HALF, C::SEGW, false>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
                 else                    sad_walk<HALF, C::SEGW, true>(Lr, Rr, Hout, nvalid - C::SEGW * s, act);
@@ -330,8 +338,8 @@ __global__ void __launch_bounds__(RingCfg<HALF>::NT, 1) sad_ring_kernel(const __
                 if (r >= nin) break;
                 const int ts = r % TR;
                 if (r >= TR) RING_WAIT(tempty + 8 * ts, (uint32_t)(r / TR - 1) & 1u, 2);
-                uint32_t* Ld = Lrep + ts * LW;
-                uint32_t* Rd = Ral + ts * RW;
+                uint32_t* Ld = Lrep + ts * C::LWS;
+                uint32_t* Rd = Ral + ts * C::RWS;
 #pragma unroll
                 for (int q = 0; q < NLQ; ++q) { const int i = lane + 32 * q; if (i < LW) Ld[i] = vl[u][q] * 0x01010101u; }
 #pragma unroll

@@ -1,6 +1,8 @@
-"""N>1 path on CPU: two gloo ranks shard one frame by row bands with a block-size halo (and a frame stream
-round-robin), gather on the host and must reproduce the single-process result bit-exactly.  The per-band
-compute here is the oracle (tests may use it); on GPUs the same partition feeds sadgpu_compute."""
+"""N>1 host logic on CPU: the partition helpers the product uses — despair.sharding.row_bands (the band / halo arithmetic of
+sadgpu_compute_sharded) and frames_for_rank (bench.py's frame sharding of the cfg5 stream) — driven by two gloo ranks with
+bench.py's barrier + max-over-ranks timing pattern.  There is no GPU here, so the per-band COMPUTE is the oracle standing in for
+the kernel: this test is evidence for the partition and the gather, not for the kernels — those are covered on real devices by
+tests/test_gpu_parity.py::test_row_band_sharding_across_devices and by bench.py's cfg4 / cfg5 legs under torchrun."""
 import os
 import socket
 
