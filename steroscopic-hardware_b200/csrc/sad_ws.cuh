@@ -30,8 +30,8 @@
 // h = 8 (block_size 16, 17: the reference's start-up default, params.go:13-18): window sums need 17 bits, the consumers keep
 // 32-bit sums (raw packed sum + high-lane sum, keys sum*512+d) while H and the ring stay 16x2-packed.
 //
-// MODE = how the walker lanes are spent, i.e. which disparity ranges fill the machine (h <= 4; h >= 5 only has mode 1 with
-// one strip):
+// MODE = how the walker lanes are spent, i.e. which disparity ranges fill the machine (h <= 4; h >= 5 has mode 1 with one strip,
+// and for h <= 7 mode 2 = 2 strips x (8 groups + tail) x 2 rows per warp for max_disparity <= 32):
 //   0: 1 strip  x 32 groups + tail  = chunks of 33 groups (132 disparity slots): max_disparity 65..128, 256 in two chunks
 //   1: 2 strips x 16 groups + tail  = 17 groups: max_disparity 33..64 (the reference's default range, params.go:13-18)
 //   2: 3 strips x  9 groups         =  9 groups: max_disparity 17..32
@@ -49,6 +49,10 @@ namespace sadgpu {
 struct WsShare { int strip, first, ng; };
 __host__ __device__ constexpr WsShare ws_share(int half, int mode, int k)
 {
+    if (half >= 5 && mode == 2) {       // 2 x 9 groups (max_disparity <= 32 at block_size 11..15): six warps per strip, 2 2 2 1 1 1
+        const int s = k / 6, i = k % 6;
+        return WsShare{s, i < 3 ? 2 * i : 3 + i, i < 3 ? 2 : 1};
+    }
     if (half >= 5) {                    // 17 groups, one strip, 1 or 2 groups per warp: the sub-partitions that carry three walker /
         // tail warps (or the loader) take fewer groups
         const int t5[12] = {2, 2, 2, 2, 1, 1, 1, 2, 1, 1, 1, 1}, t6[12] = {2, 2, 2, 2, 2, 1, 1, 1, 1, 1, 1, 1};
@@ -77,16 +81,17 @@ __host__ __device__ constexpr WsShare ws_share(int half, int mode, int k)
 }
 
 template <int HALF, int MODE> struct WsCfg {
-    static_assert(HALF >= 0 && HALF <= 8 && MODE >= 0 && MODE <= 3 && (HALF <= 4 || MODE == 1), "warp-specialised kernel: block_size <= 17");
+    static_assert(HALF >= 0 && HALF <= 8 && MODE >= 0 && MODE <= 3 && (HALF <= 4 || MODE == 1 || (MODE == 2 && HALF <= 7)),
+                  "warp-specialised kernel: block_size <= 17");
     static constexpr int WIN = 2 * HALF + 1;
     static constexpr bool WIDE = WIN * WIN * 255 >= 65536;                             // h = 8: window sums need 17 bits
     // how a candidate the reference never evaluates loses: h <= 5 a bias of 0x8000 in its running sum (sum + bias < 2^16); h = 6, 7
     // per-candidate key constants (multiplier / mask 0 and an all-ones addend); h = 8 a bias of 2^22 in its 32-bit sum
     static constexpr bool KEYC = !WIDE && WIN * WIN * 255 + 32768 >= 65536;
     static constexpr int NRW = HALF <= 4 ? 1 : 2;                                      // rows per walker warp
-    static constexpr int NS = HALF >= 5 ? 1 : MODE == 0 ? 1 : MODE == 1 ? 2 : MODE == 2 ? 3 : 6;   // strips per CTA
-    static constexpr int NGL = MODE == 0 ? 32 : MODE == 1 ? 16 : MODE == 2 ? 9 : 5;    // groups walked by the row warps
-    static constexpr bool TAIL = MODE <= 1;                                            // one more group, walked by the tail warp
+    static constexpr int NS = HALF >= 5 ? (MODE == 2 ? 2 : 1) : MODE == 0 ? 1 : MODE == 1 ? 2 : MODE == 2 ? 3 : 6;   // strips per CTA
+    static constexpr int NGL = HALF >= 5 ? (MODE == 2 ? 8 : 16) : MODE == 0 ? 32 : MODE == 1 ? 16 : MODE == 2 ? 9 : 5;  // groups walked by the row warps
+    static constexpr bool TAIL = HALF >= 5 || MODE <= 1;                               // one more group, walked by the tail warp
     static constexpr int NGC = NGL + (TAIL ? 1 : 0);                                   // groups per chunk
     static constexpr int TW = 32, TWP = 33, CW = NS * TW;                              // strip / padded strip / CTA width
     static constexpr int NSTEP = TW + 2 * HALF;                                        // steps of one strip walk

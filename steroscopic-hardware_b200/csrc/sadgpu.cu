@@ -184,8 +184,9 @@ const FastEntry kFast[8][3] = {
 // warp-specialised kernel (sad_ws.cuh): h <= 4; mode 0..3 = chunks of 33 / 17 / 9 / 5 groups on 1 / 2 / 3 / 6 strips per CTA
 // h = 5..8: mode 1 only (17 groups on one strip, two rows per walker warp)
 #define WS_ROW(H) {ws_entry<H, 0>(), ws_entry<H, 1>(), ws_entry<H, 2>(), ws_entry<H, 3>()}
-#define WS_ROW17(H) {kNoEntry, ws_entry<H, 1>(), kNoEntry, kNoEntry}
-const FastEntry kWs[9][4] = {WS_ROW(0), WS_ROW(1), WS_ROW(2), WS_ROW(3), WS_ROW(4), WS_ROW17(5), WS_ROW17(6), WS_ROW17(7), WS_ROW17(8)};
+#define WS_ROW17(H) {kNoEntry, ws_entry<H, 1>(), ws_entry<H, 2>(), kNoEntry}
+#define WS_ROW17W(H) {kNoEntry, ws_entry<H, 1>(), kNoEntry, kNoEntry}
+const FastEntry kWs[9][4] = {WS_ROW(0), WS_ROW(1), WS_ROW(2), WS_ROW(3), WS_ROW(4), WS_ROW17(5), WS_ROW17(6), WS_ROW17(7), WS_ROW17W(8)};
 
 // large-window phase-alternating kernel (sad_wide.cuh): h = 8..15, chunks of 8 groups
 const FastEntry kWide[8] = {wide_entry<8>(), wide_entry<9>(), wide_entry<10>(), wide_entry<11>(), wide_entry<12>(), wide_entry<13>(),
@@ -264,7 +265,7 @@ int choose_kernel(int B, int D, const sadgpu_tuning* t, int* variant_out, int* m
         if (!ws_supported(B)) return SADGPU_EINVAL;
         mode = ws_mode_for(ng);
         if (gpc > 0) { const int forced = gpc >= 33 ? 0 : gpc >= 17 ? 1 : gpc >= 9 ? 2 : 3; mode = std::max(mode, forced); }
-        if (half >= 5) mode = 1;                               // block_size 11..17: chunks of 17 groups
+        if (half >= 5) mode = (half <= 7 && ng <= 9 && !(gpc >= 17)) ? 2 : 1;    // block_size 11..17: chunks of 17 groups, or 2 strips x 9 groups
         fe = &kWs[half][mode];
         break;
     case V_FAST: {

@@ -53,7 +53,8 @@ def test_plans_cover_the_parameter_surface(native):
                     assert (p["NGc"], p["TW"]) in ((33, 32), (17, 64), (9, 96), (5, 192))
                     assert p["NC"] == 1 or p["NGc"] == 33            # only the 33-group layout ever chunks the range
                 else:
-                    assert B <= 17 and (p["NGc"], p["TW"]) == (17, 32) and p["RB"] == 2 * (B // 2) + 2
+                    assert B <= 17 and p["RB"] == 2 * (B // 2) + 2
+                    assert (p["NGc"], p["TW"]) == ((9, 64) if (D <= 32 and B <= 15) else (17, 32))
             else:
                 assert p["variant"] == "fast" and 10 <= B <= 15 and p["NG"] == 18
     assert despair.plan_describe(1920, 1080, 9, 128)["variant"] == "warp-specialised"

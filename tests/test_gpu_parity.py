@@ -433,7 +433,7 @@ def test_row_band_sharding_across_devices(torch_mod, oracle):
 
 
 @pytest.mark.parametrize("variant,B,D", [(2, 13, 64), (2, 9, 16), (3, 9, 128), (3, 5, 200), (3, 9, 64), (3, 7, 32), (3, 3, 16), (3, 8, 48),
-                                         (3, 11, 64), (3, 13, 128), (3, 15, 256), (3, 16, 64), (3, 17, 200), (3, 14, 16),
+                                         (3, 11, 64), (3, 13, 128), (3, 15, 256), (3, 16, 64), (3, 17, 200), (3, 14, 16), (3, 11, 32), (3, 15, 20),
                                          (4, 31, 256), (4, 16, 33),
                                          (6, 15, 256), (6, 11, 128), (6, 13, 40), (6, 31, 256), (6, 16, 64), (6, 22, 100)])
 def test_unaligned_pitch_and_odd_widths(torch_mod, ctx, oracle, variant, B, D):
@@ -456,7 +456,8 @@ def test_tma_tile_loader_matches_plain_loader(torch_mod, ctx, oracle):
     st = torch.cuda.current_stream().cuda_stream
     for (W, H, B, D, F) in [(64, 20, 9, 128, 1), (128, 37, 9, 128, 2), (320, 50, 5, 200, 3), (96, 9, 1, 68, 1), (160, 33, 8, 256, 2), (48, 70, 9, 100, 1),
                             (640, 48, 9, 64, 2), (208, 31, 7, 40, 1), (400, 25, 9, 32, 2), (112, 40, 5, 16, 3), (336, 19, 3, 8, 1),
-                            (256, 60, 11, 64, 2), (160, 45, 15, 128, 1), (192, 50, 16, 64, 2), (96, 70, 17, 256, 1), (128, 33, 13, 20, 1)]:
+                            (256, 60, 11, 64, 2), (160, 45, 15, 128, 1), (192, 50, 16, 64, 2), (96, 70, 17, 256, 1), (128, 33, 13, 20, 1),
+                            (320, 41, 15, 32, 2), (64, 30, 10, 16, 1)]:
         Ls = rng.integers(0, 256, (F, H, W), dtype=np.uint8); Rs = rng.integers(0, 256, (F, H, W), dtype=np.uint8)
         dL = torch.from_numpy(Ls).cuda(); dR = torch.from_numpy(Rs).cuda()
         for no_tma in (0, 1):
