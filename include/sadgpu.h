@@ -193,6 +193,24 @@ int  sadgpu_compute_device_batch(sadgpu_ctx *ctx, int device, int n_frames,
 int  sadgpu_gray_device(sadgpu_ctx *ctx, int device, const uint8_t *dSrc, size_t src_pitch, int channels, int mode,
                         int w, int h, uint8_t *dGray, size_t gray_pitch, void *cuda_stream);
 
+/* Post-processing hooks.  Nothing in the reference corresponds to them (cmd/handlers/stream.go:14-37 only serves
+ * the files OutputCamera writes): they are strictly additive, run only when called, and leave every entry point above bit-exact.
+ *   sadgpu_median3_device   3x3 median of a map (window clamped to the image); dDst != dSrc
+ *   sadgpu_lrcheck_device   left-right consistency: a left-map pixel (x, y) with decoded disparity d = round(v*D/255) survives iff the
+ *                           right-referenced map at (x - d, y) decodes to within `tolerance` of d; otherwise (or when x - d < 0) it
+ *                           becomes invalid_value
+ *   sadgpu_compute_checked  host call: left-referenced map (the bit-exact path), right-referenced map (the same path on the mirrored
+ *                           pair with the roles swapped), consistency check, optional median; synchronous, whole frame */
+int  sadgpu_median3_device(sadgpu_ctx *ctx, int device, const uint8_t *dSrc, size_t src_pitch, int w, int h,
+                           uint8_t *dDst, size_t dst_pitch, void *cuda_stream);
+int  sadgpu_lrcheck_device(sadgpu_ctx *ctx, int device, const uint8_t *dLeftMap, size_t left_pitch,
+                           const uint8_t *dRightMap, size_t right_pitch, int w, int h, int max_disparity, int tolerance,
+                           int invalid_value, uint8_t *dDst, size_t dst_pitch, void *cuda_stream);
+int  sadgpu_compute_checked(sadgpu_ctx *ctx, int stream,
+                            const uint8_t *left, int left_stride, const uint8_t *right, int right_stride,
+                            int w, int h, int block_size, int max_disparity, int tolerance, int invalid_value, int median,
+                            uint8_t *out, int out_stride);
+
 /* Pinned host memory from the context's pool: frames that already live here are uploaded
  * without the staging memcpy (cameras write straight into it). */
 void *sadgpu_host_alloc(sadgpu_ctx *ctx, size_t bytes);

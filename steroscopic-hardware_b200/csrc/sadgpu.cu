@@ -12,6 +12,7 @@
 #include "sad_vh.cuh"
 #endif
 #include "gray_kernels.cuh"
+#include "post_kernels.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -489,6 +490,8 @@ struct Slot {
     bool out_direct = false;
     uint8_t *hRGBA = nullptr, *dRGBA = nullptr;                // staging of the interleaved colour pair (sadgpu_compute_nrgba), lazily allocated
     size_t rgba_bytes = 0;
+    uint8_t* dPost = nullptr;                                  // five scratch planes of the post-processing hooks (sadgpu_compute_checked), lazily allocated
+    size_t post_bytes = 0;
     int cap = 1;                                               // frame pairs the buffers hold (sadgpu_reserve_batch)
     int nfr = 1;                                               // frames in flight
 };
@@ -743,7 +746,7 @@ void free_slot(Slot* s)
     if (s->done) cudaEventDestroy(s->done);
     if (s->uploaded) cudaEventDestroy(s->uploaded);
     cudaFreeHost(s->hL); cudaFreeHost(s->hOut); cudaFreeHost(s->hRGBA);
-    cudaFree(s->dL); cudaFree(s->dOut); cudaFree(s->gkey); cudaFree(s->dRGBA);
+    cudaFree(s->dL); cudaFree(s->dOut); cudaFree(s->gkey); cudaFree(s->dRGBA); cudaFree(s->dPost);
     delete s;
 }
 
@@ -1331,6 +1334,80 @@ int sadgpu_gray_device(sadgpu_ctx* c, int device, const uint8_t* dSrc, size_t sr
     else                                                  gray_kernel<GRAY_RGBX8_LOADPNG, 3><<<grid, block, 0, s>>>(dSrc, src_pitch, dGray, gray_pitch, w, h, vec_ok);
     e = cudaGetLastError();
     return e == cudaSuccess ? SADGPU_OK : (int)e;
+}
+
+// ---- post-processing hooks: additive, never on the bit-exact path ----
+int sadgpu_median3_device(sadgpu_ctx* c, int device, const uint8_t* dSrc, size_t src_pitch, int w, int h, uint8_t* dDst, size_t dst_pitch,
+                          void* cuda_stream)
+{
+    if (!c || !dSrc || !dDst || dSrc == dDst || w <= 0 || h <= 0 || src_pitch < (size_t)w || dst_pitch < (size_t)w) return SADGPU_EINVAL;
+    if (device < 0 || device >= (int)c->devices.size()) return SADGPU_ERANGE;
+    cudaError_t e = cudaSetDevice(c->devices[device]);
+    if (e != cudaSuccess) return (int)e;
+    median3_kernel<<<dim3(ceil_div(w, 256), h), 256, 0, (cudaStream_t)cuda_stream>>>(dSrc, src_pitch, dDst, dst_pitch, w, h);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? SADGPU_OK : (int)e;
+}
+
+int sadgpu_lrcheck_device(sadgpu_ctx* c, int device, const uint8_t* dLeftMap, size_t left_pitch, const uint8_t* dRightMap, size_t right_pitch,
+                          int w, int h, int max_disparity, int tolerance, int invalid_value, uint8_t* dDst, size_t dst_pitch, void* cuda_stream)
+{
+    if (!c || !dLeftMap || !dRightMap || !dDst || w <= 0 || h <= 0 || left_pitch < (size_t)w || right_pitch < (size_t)w || dst_pitch < (size_t)w)
+        return SADGPU_EINVAL;
+    if (max_disparity < 1 || max_disparity > SADGPU_MAX_DISPARITY || tolerance < 0 || invalid_value < 0 || invalid_value > 255) return SADGPU_EINVAL;
+    if (device < 0 || device >= (int)c->devices.size()) return SADGPU_ERANGE;
+    cudaError_t e = cudaSetDevice(c->devices[device]);
+    if (e != cudaSuccess) return (int)e;
+    lrcheck_kernel<<<dim3(ceil_div(w, 256), h), 256, 0, (cudaStream_t)cuda_stream>>>(dLeftMap, left_pitch, dRightMap, right_pitch, dDst, dst_pitch,
+                                                                                   w, h, max_disparity, tolerance, invalid_value);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? SADGPU_OK : (int)e;
+}
+
+int sadgpu_compute_checked(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, const uint8_t* r, int rs, int w, int h, int B, int D,
+                           int tolerance, int invalid_value, int median, uint8_t* out, int out_stride)
+{
+    int rc = check_io(c, stream, l, ls, r, rs, w, h);
+    if (rc) return rc;
+    if (!out || out_stride < w || tolerance < 0 || invalid_value < 0 || invalid_value > 255) return SADGPU_EINVAL;
+    if ((rc = validate(w, h, B, D, 0, h))) return rc;
+    Slot* s = c->slots[stream];
+    std::lock_guard<std::mutex> g(s->mu);
+    if (s->busy) return SADGPU_EBUSY;
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e != cudaSuccess) return (int)e;
+    const size_t pitch = (size_t)round_up(w, 4), plane = pitch * (size_t)h;
+    if (s->post_bytes < 5 * plane) {
+        cudaStreamSynchronize(s->st);
+        cudaFree(s->dPost); s->dPost = nullptr; s->post_bytes = 0;
+        if ((e = cudaMalloc((void**)&s->dPost, 5 * plane)) != cudaSuccess) return (int)e;
+        s->post_bytes = 5 * plane;
+    }
+    s->pitch = pitch; s->dR = s->dL + plane; s->hR = s->hL + plane;
+    if ((rc = upload(c, s, l, ls, s->hL, s->dL, w, 0, h))) return rc;
+    if ((rc = upload(c, s, r, rs, s->hR, s->dR, w, 0, h))) return rc;
+    uint8_t *mL = s->dPost, *mR = mL + plane, *mapRm = mR + plane, *mapR = mapRm + plane, *tmp = mapR + plane;
+    const dim3 grid(ceil_div(w, 256), h);
+    // left-referenced map (the bit-exact path), then the right-referenced one: the same path on the mirrored pair with the roles swapped
+    Job jl{s->dL, pitch, 0, s->dR, pitch, 0, s->dOut, pitch, 0, 1, w, h, B, D, 0, h};
+    if ((rc = run_job(c, s->dev_index, jl, nullptr, s->gkey, s->st))) { cudaStreamSynchronize(s->st); return rc; }
+    mirror_kernel<<<grid, 256, 0, s->st>>>(s->dR, pitch, mL, pitch, w, h);
+    mirror_kernel<<<grid, 256, 0, s->st>>>(s->dL, pitch, mR, pitch, w, h);
+    Job jr{mL, pitch, 0, mR, pitch, 0, mapRm, pitch, 0, 1, w, h, B, D, 0, h};
+    if ((rc = run_job(c, s->dev_index, jr, nullptr, s->gkey, s->st))) { cudaStreamSynchronize(s->st); return rc; }
+    mirror_kernel<<<grid, 256, 0, s->st>>>(mapRm, pitch, mapR, pitch, w, h);
+    lrcheck_kernel<<<grid, 256, 0, s->st>>>(s->dOut, pitch, mapR, pitch, tmp, pitch, w, h, D, tolerance, invalid_value);
+    const uint8_t* result = tmp;
+    if (median) { median3_kernel<<<grid, 256, 0, s->st>>>(tmp, pitch, mapRm, pitch, w, h); result = mapRm; }
+    if ((e = cudaGetLastError()) != cudaSuccess) { cudaStreamSynchronize(s->st); return (int)e; }
+    const bool direct = in_pool(c, out, (size_t)(h - 1) * out_stride + w);
+    uint8_t* dst = direct ? out : s->hOut;
+    const size_t dpitch = direct ? (size_t)out_stride : pitch;
+    e = cudaMemcpy2DAsync(dst, dpitch, result, pitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToHost, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) return (int)e;
+    if (!direct) c->copier->copy(out, (size_t)out_stride, s->hOut, pitch, (size_t)w, (size_t)h);
+    return SADGPU_OK;
 }
 
 void* sadgpu_host_alloc(sadgpu_ctx* c, size_t bytes)

@@ -47,6 +47,11 @@ EXPORTS = {
                                             c_size_t, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_size_t,
                                             c_size_t, c_void_p, ctypes.POINTER(Tuning)]),
     "sadgpu_gray_device": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "sadgpu_median3_device": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "sadgpu_lrcheck_device": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_size_t, c_void_p]),
+    "sadgpu_compute_checked": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, c_void_p, c_int]),
     "sadgpu_host_alloc": (c_void_p, [c_void_p, c_size_t]),
     "sadgpu_host_free": (None, [c_void_p, c_void_p]),
     "sadgpu_debug_read": (c_int, [c_void_p, c_int, ctypes.POINTER(ctypes.c_uint32), c_int]),

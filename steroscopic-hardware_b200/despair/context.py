@@ -184,6 +184,25 @@ class Context:
         """Go-exact luma on the device (modes: 0 NRGBA generic path, 1 opaque RGB intended, 2 LoadPNG-as-written)."""
         N.check(self._L.sadgpu_gray_device(self._h, device, dSrc, src_pitch, channels, mode, w, h, dGray, gray_pitch, cuda_stream))
 
+    # -- post-processing hooks (additive, SURVEY.md §8(f) N4) -------------------------------
+    def compute_checked(self, left, right, block_size, max_disparity, tolerance=1, invalid_value=0, median=False, stream=0, out=None):
+        """Left-right consistency checked (and optionally 3x3 median filtered) disparity map; NOT part of the bit-exact path."""
+        l, r = _pair(left, right)
+        h, w = l.shape
+        out = _out_2d(out, (h, w))
+        N.check(self._L.sadgpu_compute_checked(self._h, stream, l.ctypes.data, l.strides[0], r.ctypes.data, r.strides[0], w, h,
+                                                block_size, max_disparity, tolerance, invalid_value, int(bool(median)),
+                                                out.ctypes.data, out.strides[0]))
+        return out
+
+    def median3_device(self, dSrc, src_pitch, w, h, dDst, dst_pitch, device=0, cuda_stream=0):
+        N.check(self._L.sadgpu_median3_device(self._h, device, dSrc, src_pitch, w, h, dDst, dst_pitch, cuda_stream))
+
+    def lrcheck_device(self, dLeft, left_pitch, dRight, right_pitch, w, h, max_disparity, tolerance, invalid_value, dDst, dst_pitch,
+                       device=0, cuda_stream=0):
+        N.check(self._L.sadgpu_lrcheck_device(self._h, device, dLeft, left_pitch, dRight, right_pitch, w, h, max_disparity, tolerance,
+                                               invalid_value, dDst, dst_pitch, cuda_stream))
+
     # -- pinned pool -----------------------------------------------------------------------
     def host_array(self, shape):
         n = int(np.prod(shape))

@@ -22,7 +22,7 @@ def native():
 def test_header_symbols_all_exported(native):
     hdr = open(os.path.join(ROOT, "include", "sadgpu.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    declared = set(re.findall(r"\b(sadgpu_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(sadgpu_[a-z0-9_]+)\s*\(", hdr))
     assert declared, "no declarations parsed"
     L = ctypes.CDLL(native.LIB_PATH)
     missing = [s for s in sorted(declared) if not hasattr(L, s)]

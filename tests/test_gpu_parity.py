@@ -649,3 +649,37 @@ def test_wait_uploaded_releases_pinned_inputs(ctx, oracle):
         pl[:] = 0; pr[:] = 255                              # the next capture overwrites the frame
         ctx.wait(t)
         assert np.array_equal(out, oracle.frame_box(L, R, 9, 128))
+
+
+def test_post_processing_hooks_are_additive(torch_mod, ctx, oracle):
+    """SURVEY §8(f) N4: 3x3 median and left-right consistency on the device against their numpy statement (oracle/post_numpy.py);
+    the hooks leave the bit-exact entry points untouched."""
+    from oracle import post_numpy as P
+    torch = torch_mod
+    rng = np.random.default_rng(50)
+    st = torch.cuda.current_stream().cuda_stream
+    for (h, w) in [(37, 101), (64, 256), (5, 3), (1, 1)]:
+        m = rng.integers(0, 256, (h, w), dtype=np.uint8); m2 = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        d = torch.from_numpy(m).cuda(); d2 = torch.from_numpy(m2).cuda(); o = torch.zeros_like(d)
+        ctx.median3_device(d.data_ptr(), w, w, h, o.data_ptr(), w, cuda_stream=st)
+        torch.cuda.synchronize()
+        assert np.array_equal(o.cpu().numpy(), P.median3(m)), (h, w)
+        for (D, tol, inv) in ((64, 1, 0), (256, 0, 255), (16, 2, 7)):
+            ctx.lrcheck_device(d.data_ptr(), w, d2.data_ptr(), w, w, h, D, tol, inv, o.data_ptr(), w, cuda_stream=st)
+            torch.cuda.synchronize()
+            assert np.array_equal(o.cpu().numpy(), P.lr_check(m, m2, D, tol, inv)), (h, w, D, tol)
+    # the host call: both maps through the bit-exact path, check, median
+    base = rng.integers(0, 256, (90, 260), dtype=np.uint8)
+    L = np.ascontiguousarray(base[:, 40:240]); R = np.ascontiguousarray(np.roll(base, -12, 1)[:, 40:240])
+    for (B, D, med) in ((9, 64, False), (16, 64, True), (5, 32, True)):
+        lm = oracle.frame_box(L, R, B, D)
+        rm = P.right_referenced(oracle.frame_box, L, R, B, D)
+        exp = P.lr_check(lm, rm, D, 1, 0)
+        if med:
+            exp = P.median3(exp)
+        assert np.array_equal(ctx.compute_checked(L, R, B, D, tolerance=1, invalid_value=0, median=med), exp), (B, D, med)
+        assert np.array_equal(ctx.compute(L, R, B, D), lm)                     # the plain path is what it was
+    # on a clean shifted pair the check keeps the interior and removes the left band where the match leaves the image
+    got = ctx.compute_checked(L, R, 9, 64, tolerance=1, invalid_value=0)
+    d12 = 12 * 255 // 64
+    assert (got[10:-10, 90:190] == d12).mean() > 0.95
