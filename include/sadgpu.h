@@ -67,10 +67,14 @@ typedef struct sadgpu_tuning {
                                3 = warp-specialised kernel (block_size <= 9; the default there: chunks of 33 / 17 / 9 / 5 disparity groups
                                    on 1 / 2 / 3 / 6 column strips per CTA, by max_disparity),
                                4 = phase-alternating large-window kernel (block_size 16..31),
-                               6 = H-ring mbarrier-pipelined kernel (block_size 10..31; the default there whenever it needs fewer passes over the
-                                   disparity range than variants 2 / 4).  1 and 5 (removed kernels) are rejected. */
+                               6 = H-ring mbarrier-pipelined kernel (block_size 10..31),
+                               7 = warp-specialised kernel with a shared-memory ring (block_size 10..31; the default for block_size >= 18 and
+                                   for block_size 16, 17 with max_disparity <= 32).  It loads its tiles with TMA only: images whose base,
+                                   pitch or frame stride is not a multiple of 16 bytes take variant 6 or 4 instead.
+                               1 and 5 (removed kernels) are rejected. */
     int reserved[4];        /* [0]: frames per launch (sadgpu_plan_describe only); [1]: developer flags (profile builds of the ring kernel);
-                               [2] = 1: do not use TMA tile loads in the warp-specialised kernel */
+                               [2] = 1: do not use TMA tile loads in the warp-specialised kernel; = 2: fail with SADGPU_EINVAL
+                               instead of substituting another kernel when variant 7 cannot use TMA */
 } sadgpu_tuning;
 
 int  sadgpu_device_count(void);

@@ -39,6 +39,9 @@
 #pragma once
 #include "sad_common.cuh"
 
+#ifndef WS_REGS_SMALL
+#define WS_REGS_SMALL 40    // walker registers of the h <= 4 instances (setmaxnreg)
+#endif
 #ifndef WS_SKIP
 #define WS_SKIP 0       // developer timing experiments (results wrong): 1 = walkers idle, 2 = consumers idle, 4 = tail walker idle
 #endif
@@ -118,7 +121,7 @@ template <int HALF, int MODE> struct WsCfg {
     static constexpr int REGS_LAUNCH = 80, REGS_PROD = 56, REGS_CONS = 104;
     // with TMA the walkers carry no prefetch state; setmaxnreg moves registers inside the CTA's launch allocation.  A walk keeps the
     // 2h+1 old terms of both packed sums in registers: 40 registers hold a 9-wide window, the 11..17-wide ones need 48 / 56
-    static constexpr int REGS_PROD_TMA = HALF <= 4 ? 40 : HALF <= 6 ? 48 : 56, REGS_CONS_TMA = 160 - REGS_PROD_TMA;
+    static constexpr int REGS_PROD_TMA = HALF <= 4 ? WS_REGS_SMALL : HALF <= 6 ? 48 : 56, REGS_CONS_TMA = 160 - REGS_PROD_TMA;
     static constexpr int OFF = walk_off(HALF);
     static constexpr int NWALKW = walk_words(HALF, NSTEP);
     static constexpr int RW = NGC - 1 + (TW / 4) * (NS - 1) + NWALKW;       // aligned right words per tile row

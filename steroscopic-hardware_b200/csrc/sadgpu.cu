@@ -7,6 +7,7 @@
 #include "sad_ws.cuh"
 #include "sad_wide.cuh"
 #include "sad_ring.cuh"
+#include "sad_wsr.cuh"
 #ifdef SADGPU_DEV_VARIANTS          // developer builds only: the first correct kernel and the vertical-first experiment (cross-checks)
 #include "sad_kernels.cuh"
 #include "sad_vh.cuh"
@@ -58,7 +59,7 @@ int validate(int w, int h, int B, int D, int y0, int y1)
 }
 
 // kernel_variant values of sadgpu_tuning
-enum { V_AUTO = 0, V_GENERIC = 1, V_FAST = 2, V_WS = 3, V_WIDE = 4, V_VH = 5, V_RING = 6 };
+enum { V_AUTO = 0, V_GENERIC = 1, V_FAST = 2, V_WS = 3, V_WIDE = 4, V_VH = 5, V_RING = 6, V_WSR = 7 };
 
 // ---------------------------------------------------------------------------------------
 // Kernel table.  Every production kernel takes FastArgs and a grid (column strips, row bands, frames x chunks).
@@ -145,6 +146,20 @@ cudaError_t launch_ring(const FastPlan& p, cudaStream_t s)
     return cudaGetLastError();
 }
 
+template <int HALF>
+cudaError_t launch_wsr(const FastPlan& p, cudaStream_t s)
+{
+    using C = WsrCfg<HALF>;
+    static_assert(C::SMEM <= kSmemBudget, "shared-memory-ring warp-specialised kernel does not fit shared memory");
+    static std::atomic<unsigned long long> done{0};
+    auto k = sad_wsr_kernel<HALF>;
+    cudaError_t e = ensure_smem(k, C::SMEM, &done);
+    if (e != cudaSuccess) return e;
+    if (!p.a.use_tma) return cudaErrorInvalidValue;            // run_job re-plans onto another kernel when TMA cannot be used
+    k<<<p.grid, C::NT, C::SMEM, s>>>(p.a);
+    return cudaGetLastError();
+}
+
 template <int HALF, int NGC> constexpr FastEntry fast_entry()
 {
     using C = FastCfg<HALF, NGC>;
@@ -167,6 +182,13 @@ template <int HALF> constexpr FastEntry ring_entry()
 {
     using C = RingCfg<HALF>;
     if constexpr (dev_on(HALF)) return FastEntry{launch_ring<HALF>, C::NT, C::SMEM, 4, C::TW, C::NGC, 0, 0};
+    else return kNoEntry;
+}
+
+template <int HALF> constexpr FastEntry wsr_entry()
+{
+    using C = WsrCfg<HALF>;
+    if constexpr (dev_on(HALF)) return FastEntry{launch_wsr<HALF>, C::NT, C::SMEM, C::RB, C::CW, C::NGC, C::LBOX, C::RWT * 4};
     else return kNoEntry;
 }
 
@@ -196,6 +218,10 @@ const FastEntry kWide[8] = {wide_entry<8>(), wide_entry<9>(), wide_entry<10>(), 
 // shared-memory-ring warp-specialised kernel (sad_ring.cuh): h = 5..15, 32-column strips, chunks of 33 groups (h <= 7) or 17
 const FastEntry kRing[11] = {ring_entry<5>(), ring_entry<6>(), ring_entry<7>(), ring_entry<8>(), ring_entry<9>(), ring_entry<10>(),
                              ring_entry<11>(), ring_entry<12>(), ring_entry<13>(), ring_entry<14>(), ring_entry<15>()};
+
+// warp-specialised kernel with a shared-memory ring (sad_wsr.cuh): h = 5..15, 32-column strips, chunks of 9 groups; needs TMA
+const FastEntry kWsr[11] = {wsr_entry<5>(), wsr_entry<6>(), wsr_entry<7>(), wsr_entry<8>(), wsr_entry<9>(), wsr_entry<10>(),
+                            wsr_entry<11>(), wsr_entry<12>(), wsr_entry<13>(), wsr_entry<14>(), wsr_entry<15>()};
 
 #ifdef SADGPU_DEV_VARIANTS
 template <int HALF>
@@ -227,6 +253,7 @@ bool ring_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
 bool fast_supported(int B) { return B / 2 <= 7; }
 bool wide_supported(int B) { return B / 2 >= 8 && B / 2 <= 15; }
 bool ws_supported(int B) { return B / 2 <= 8; }
+bool wsr_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
 
 // Planner default for block_size >= 10, from the measured variant sweep (profiles/r01_variant_sweep.json, inputs streaming
 // from HBM): a ring pass over 33 groups costs about 1.7x a pass of the phase-alternating kernel over 18 groups, a ring pass
@@ -248,14 +275,17 @@ int choose_kernel(int B, int D, const sadgpu_tuning* t, int* variant_out, int* m
     const int half = B / 2, ng = (D + 4) / 4;
     int variant = t ? t->kernel_variant : V_AUTO;
     const int gpc = t ? t->groups_per_chunk : 0;               // tests: force smaller chunks
-    if (variant < 0 || variant > 6) return SADGPU_EINVAL;
+    if (variant < 0 || variant > 7) return SADGPU_EINVAL;
     if (variant == V_AUTO) {
         // measured (profiles/r02_*): the warp-specialised kernel wins for every block_size <= 17 except where another kernel
         // covers the whole range in ONE pass that two 17-group chunks cannot beat: 18 groups (max_disparity 65..68) at block_size
         // 11..15 (phase-alternating kernel, 18-group instance) and <= 8 groups (max_disparity <= 28) at block_size 16, 17
+        // block_size >= 18, and <= 9 groups at block_size 16, 17: the warp-specialised kernel with the shared-memory ring (it falls
+        // back to the mbarrier-pipelined ring kernel in run_job when TMA cannot address the images)
         if (half <= 4) variant = V_WS;
         else if (half <= 7 && ng != 18) variant = V_WS;
-        else if (half == 8 && ng >= 9) variant = V_WS;
+        else if (half == 8 && ng > 9) variant = V_WS;
+        else if (half >= 8) variant = V_WSR;
         else if (ring_auto(B, D)) variant = V_RING;
         else variant = fast_supported(B) ? V_FAST : V_WIDE;
     }
@@ -286,6 +316,10 @@ int choose_kernel(int B, int D, const sadgpu_tuning* t, int* variant_out, int* m
         if (!ring_supported(B)) return SADGPU_EINVAL;
         fe = &kRing[half - 5];
         break;
+    case V_WSR:
+        if (!wsr_supported(B)) return SADGPU_EINVAL;
+        fe = &kWsr[half - 5];
+        break;
 #ifdef SADGPU_DEV_VARIANTS
     case V_VH:
         if (!vh_supported(B)) return SADGPU_EINVAL;
@@ -303,7 +337,7 @@ int choose_kernel(int B, int D, const sadgpu_tuning* t, int* variant_out, int* m
 const char* variant_name(int v)
 {
     switch (v) { case V_GENERIC: return "generic"; case V_FAST: return "fast"; case V_WS: return "warp-specialised"; case V_WIDE: return "wide";
-                 case V_VH: return "vertical-first"; case V_RING: return "ring"; default: return "?"; }
+                 case V_VH: return "vertical-first"; case V_RING: return "ring"; case V_WSR: return "warp-specialised, shared-memory ring"; default: return "?"; }
 }
 
 int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, const sadgpu_tuning* t, int sm_count, FastPlan* p)
@@ -335,7 +369,7 @@ int make_fast_plan(int w, int h, int B, int D, int y0, int y1, int n_frames, con
             const long ctas = (long)nstrips * nb * a.NC * n_frames;
             const long waves = (ctas + sm_count - 1) / sm_count;
             // rows a CTA spends on pipeline fill and drain, beyond its band and the window halo
-            const int fill = p->variant == V_WS ? 2 * fe->rb : (p->variant == V_RING || p->variant == V_VH) ? 12 : fe->rb / 2 + 2;
+            const int fill = (p->variant == V_WS || p->variant == V_WSR) ? 2 * fe->rb : (p->variant == V_RING || p->variant == V_VH) ? 12 : fe->rb / 2 + 2;
             const long cost = waves * (round_up(bh + 2 * half, fe->rb) + fill);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; nbands = nb; }
         }
@@ -564,6 +598,20 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
     int rc = make_fast_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, j.n_frames, t, c->sm_count[dev_index], &p);
     if (rc) return rc;
     if (j.y1 == j.y0) return SADGPU_OK;
+    bool tma_ok = false;
+    if ((p.variant == V_WS || p.variant == V_WSR) && !(t && t->reserved[2] == 1))      // reserved[2] == 1: force the non-TMA loader (tests)
+        tma_ok = make_tmap(&p.a.tmapL, j.dL, j.w, j.h, j.pitchL, j.frameL, j.n_frames, p.fe->lbox, p.fe->rb) &&
+                 make_tmap(&p.a.tmapR, j.dR, j.w, j.h, j.pitchR, j.frameR, j.n_frames, p.fe->rbox, p.fe->rb);
+    if (p.variant == V_WSR && !tma_ok && t && t->reserved[2] == 2) return SADGPU_EINVAL;     // tests: no silent substitution
+    if (p.variant == V_WSR && !tma_ok) {
+        // the shared-memory-ring warp-specialised kernel has no plain-load path: images TMA cannot address (base, pitch or frame
+        // stride not a multiple of 16 bytes) take the mbarrier-pipelined ring kernel
+        sadgpu_tuning t2{};
+        if (t) t2 = *t;
+        // what the planner chose before this kernel existed: ring or wide by the measured pass costs
+        t2.kernel_variant = ring_auto(j.B, j.D) ? V_RING : V_WIDE; t2.groups_per_chunk = 0;
+        if ((rc = make_fast_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, j.n_frames, &t2, c->sm_count[dev_index], &p))) return rc;
+    }
     const FastEntry* fe = p.fe;
     const int variant = p.variant;
     FastArgs& a = p.a;
@@ -572,12 +620,7 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
     a.frameL = j.frameL; a.frameR = j.frameR; a.frameOut = j.frameOut;
     a.k65536 = 65536u;
     a.debug_skip = t ? t->reserved[1] : 0;
-    a.use_tma = 0;
-    if (variant == V_WS && !(t && t->reserved[2] == 1)) {                 // reserved[2] == 1: force the non-TMA loader (tests)
-        if (make_tmap(&a.tmapL, j.dL, j.w, j.h, j.pitchL, j.frameL, j.n_frames, fe->lbox, fe->rb) &&
-            make_tmap(&a.tmapR, j.dR, j.w, j.h, j.pitchR, j.frameR, j.n_frames, fe->rbox, fe->rb))
-            a.use_tma = 1;
-    }
+    a.use_tma = tma_ok ? 1 : 0;
     a.aligned = ((uintptr_t)j.dR % 4 == 0 && j.pitchR % 4 == 0 && j.frameR % 4 == 0) ? 1 : 0;
     if (a.debug_skip & 4) { uint32_t* gk = nullptr; rc = ensure_dbg(c, dev_index, &gk); if (rc) return rc; a.gkey = gk; }
     bool async_scratch = false;
@@ -594,8 +637,10 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
     }
     cudaError_t e = fe->fn(p, s);
     if (e == cudaSuccess && a.NC > 1) {
-        dim3 g(ceil_div(j.w, 256), j.y1 - j.y0, j.n_frames);
-        sad_finalize_kernel<<<g, 256, 0, s>>>(a.gkey, j.dOut, j.w, j.h, j.y0, j.y1, (int)j.pitchOut, j.frameOut, j.D);
+        const int vec4 = (j.w % 4 == 0 && (uintptr_t)j.dOut % 4 == 0 && j.pitchOut % 4 == 0 && j.frameOut % 4 == 0 && (uintptr_t)a.gkey % 16 == 0) ? 1 : 0;
+        dim3 g(ceil_div(j.w, vec4 ? 1024 : 256), j.y1 - j.y0, j.n_frames);
+        const uint32_t magic = j.D > 1 ? (uint32_t)((1ull << 32) / (unsigned)j.D + 1ull) : 0u;
+        sad_finalize_kernel<<<g, 256, 0, s>>>(a.gkey, j.dOut, j.w, j.h, j.y0, j.y1, (int)j.pitchOut, j.frameOut, j.D, magic, vec4);
         e = cudaGetLastError();
     }
     if (async_scratch) { cudaError_t e2 = cudaFreeAsync(a.gkey, s); if (e == cudaSuccess) e = e2; }   // stream-ordered: after the kernels above

@@ -44,10 +44,8 @@ def test_plans_cover_the_parameter_surface(native):
             p = despair.plan_describe(1920, 1080, B, D)
             assert p["half"] == B // 2 and p["smem"] <= 232448 and p["NC"] * p["NGc"] >= p["NG"]
             assert p["grid"][0] * p["TW"] >= 1920
-            if p["variant"] == "wide":
-                assert 16 <= B <= 31
-            elif p["variant"] == "ring":
-                assert 18 <= B <= 31 and p["TW"] == 32 and p["NGc"] == 17
+            if p["variant"] == "warp-specialised, shared-memory ring":
+                assert (B >= 18 or (B >= 16 and D <= 32)) and (p["NGc"], p["TW"], p["RB"]) == (9, 32, 10)
             elif p["variant"] == "warp-specialised":
                 if B <= 9:
                     assert (p["NGc"], p["TW"]) in ((33, 32), (17, 64), (9, 96), (5, 192))
@@ -62,14 +60,18 @@ def test_plans_cover_the_parameter_surface(native):
     assert despair.plan_describe(1920, 1080, 9, 16)["NGc"] == 5
     assert despair.plan_describe(1920, 1080, 15, 256)["variant"] == "warp-specialised"     # cfg2: four chunks of 17 groups
     assert despair.plan_describe(1920, 1080, 15, 68)["variant"] == "fast"
-    assert despair.plan_describe(1920, 1080, 31, 256)["variant"] == "ring"
-    assert despair.plan_describe(1920, 1080, 31, 16)["variant"] == "wide"
-    assert despair.plan_describe(1920, 1080, 16, 16)["variant"] == "wide"
+    assert despair.plan_describe(1920, 1080, 31, 256)["variant"] == "warp-specialised, shared-memory ring"   # cfg4: eight chunks of 9 groups
+    assert despair.plan_describe(1920, 1080, 31, 16)["variant"] == "warp-specialised, shared-memory ring"
+    assert despair.plan_describe(1920, 1080, 16, 16)["variant"] == "warp-specialised, shared-memory ring"
+    assert despair.plan_describe(1920, 1080, 31, 256, tuning=dict(kernel_variant=6))["variant"] == "ring"
+    assert despair.plan_describe(1920, 1080, 31, 16, tuning=dict(kernel_variant=4))["variant"] == "wide"
     assert despair.plan_describe(1920, 1080, 16, 64)["variant"] == "warp-specialised"     # the reference's start-up parameters (params.go:13-18)
     with pytest.raises(despair.SadGpuError):
         despair.plan_describe(1920, 1080, 31, 256, tuning=dict(kernel_variant=2))      # phase-alternating kernel needs block_size <= 15
     with pytest.raises(despair.SadGpuError):
         despair.plan_describe(1920, 1080, 19, 64, tuning=dict(kernel_variant=3))       # warp-specialised kernel needs block_size <= 17
+    with pytest.raises(despair.SadGpuError):
+        despair.plan_describe(1920, 1080, 9, 64, tuning=dict(kernel_variant=7))        # its shared-memory-ring form needs block_size >= 10
     for gone in (1, 5):                                                               # removed kernels are rejected, not substituted
         with pytest.raises(despair.SadGpuError):
             despair.plan_describe(1920, 1080, 15, 64, tuning=dict(kernel_variant=gone))

@@ -123,6 +123,52 @@ def test_every_kernel_variant_agrees_with_oracle(torch_mod, ctx, oracle, variant
         assert np.array_equal(got, oracle.frame_box(L, R, B, D)), (W, H, B, D, variant)
 
 
+STRICT_WSR = dict(kernel_variant=7, reserved=(0, 0, 2, 0))       # reserved[2] = 2: fail instead of substituting another kernel
+
+
+@pytest.mark.parametrize("B", list(range(10, 32)))
+def test_shared_ring_warp_specialised_kernel(torch_mod, ctx, oracle, B):
+    """variant 7 (the planner's choice for block_size >= 18): widths that are multiples of 16 so that TMA addresses the images, and
+    the strict flag, so that a silent substitution of another kernel would fail the test.  One chunk (D <= 32), chunked ranges,
+    forced bands shorter than a batch / the window, every image kind."""
+    rng = np.random.default_rng(700 + B)
+    for i, D in enumerate((16, 32, 36, 64, 100, 255, 256)):
+        W = 16 * int(rng.integers(2, 24)); H = int(rng.integers(8, 90))
+        L, R = synth_pair(rng, H, W, (i + B) % 5)
+        tun = dict(STRICT_WSR)
+        if i % 2:
+            tun["band_rows"] = int(rng.integers(1, 40))
+        assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, tun), oracle.frame_box(L, R, B, D)), (W, H, B, D, tun)
+
+
+def test_shared_ring_kernel_row_ranges_frames_and_fallback(torch_mod, ctx, oracle):
+    import despair
+    torch = torch_mod
+    rng = np.random.default_rng(77)
+    # row ranges [y0, y1) of a frame (RunSad tiles / row-band sharding)
+    L, R = synth_pair(rng, 97, 208, 1)
+    exp = oracle.frame_box(L, R, 25, 64)
+    for (y0, y1) in ((0, 97), (0, 1), (13, 14), (5, 60), (60, 97), (96, 97)):
+        got = dev_run(torch_mod, ctx, L, R, 25, 64, STRICT_WSR, y0=y0, y1=y1)
+        assert np.array_equal(got[y0:y1], exp[y0:y1]) and (got[:y0] == 77).all() and (got[y1:] == 77).all(), (y0, y1)
+    # several frames per launch (TMA walks the frame axis), one and several chunks
+    for (F, H, W, B, D) in [(3, 41, 96, 31, 32), (4, 33, 160, 19, 200), (2, 70, 64, 16, 20)]:
+        pairs = [synth_pair(rng, H, W, k % 5) for k in range(F)]
+        dL = torch.from_numpy(np.stack([p[0] for p in pairs])).cuda(); dR = torch.from_numpy(np.stack([p[1] for p in pairs])).cuda()
+        dO = torch.zeros_like(dL)
+        ctx.compute_device_batch(F, dL.data_ptr(), W, W * H, dR.data_ptr(), W, W * H, W, H, B, D, dO.data_ptr(), W, W * H,
+                                 cuda_stream=torch.cuda.current_stream().cuda_stream, tuning=STRICT_WSR)
+        torch.cuda.synchronize()
+        for f in range(F):
+            assert np.array_equal(dO[f].cpu().numpy(), oracle.frame_box(pairs[f][0], pairs[f][1], B, D)), (F, H, W, B, D, f)
+    # images TMA cannot address: the strict flag reports it, the default substitutes the ring / wide kernel (same pixels)
+    L, R = synth_pair(rng, 40, 131, 0)
+    with pytest.raises(despair.SadGpuError):
+        dev_run(torch_mod, ctx, L, R, 31, 64, STRICT_WSR)
+    for (B, D) in ((31, 64), (19, 16), (16, 32)):
+        assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, dict(kernel_variant=7)), oracle.frame_box(L, R, B, D)), (B, D)
+
+
 def test_batched_frames_one_launch(torch_mod, ctx, oracle):
     torch = torch_mod
     rng = np.random.default_rng(61)
@@ -435,7 +481,8 @@ def test_row_band_sharding_across_devices(torch_mod, oracle):
 @pytest.mark.parametrize("variant,B,D", [(2, 13, 64), (2, 9, 16), (3, 9, 128), (3, 5, 200), (3, 9, 64), (3, 7, 32), (3, 3, 16), (3, 8, 48),
                                          (3, 11, 64), (3, 13, 128), (3, 15, 256), (3, 16, 64), (3, 17, 200), (3, 14, 16), (3, 11, 32), (3, 15, 20),
                                          (4, 31, 256), (4, 16, 33),
-                                         (6, 15, 256), (6, 11, 128), (6, 13, 40), (6, 31, 256), (6, 16, 64), (6, 22, 100)])
+                                         (6, 15, 256), (6, 11, 128), (6, 13, 40), (6, 31, 256), (6, 16, 64), (6, 22, 100),
+                                         (7, 31, 256), (7, 19, 32), (7, 16, 16)])
 def test_unaligned_pitch_and_odd_widths(torch_mod, ctx, oracle, variant, B, D):
     """Pitches that are not multiples of 4 disable the aligned 32-bit tile loads; widths that are not multiples of the
     strip width exercise the right-edge masking (sad.go:231-233) in every kernel."""

@@ -26,7 +26,7 @@ out = []
 for B in (int(b) for b in os.environ.get("BS", "10,11,13,15,16,17,21,25,31").split(",")):
     for D in (16, 32, 48, 64, 80, 96, 128, 192, 256):
         row = {"B": B, "D": D, "auto": t(B, D, 0), "auto_variant": despair.plan_describe(W, H, B, D, frames=F)["variant"]}
-        for v, name in ((2, "fast"), (4, "wide"), (5, "vh"), (6, "ring")):
+        for v, name in ((2, "fast"), (3, "ws"), (4, "wide"), (6, "ring"), (7, "wsr")):
             row[name] = t(B, D, v)
         out.append(row); print(row, flush=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "variant_sweep.json"), "w"), indent=1)

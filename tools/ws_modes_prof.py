@@ -17,7 +17,7 @@ for B in BS:
         from oracle import oracle as O
         bad = 0
         for D in DS:
-            for (hh, ww) in ((37, 200), (64, 333)):
+            for (hh, ww) in ((37, 208), (64, 336), (37, 200), (45, 32)):
                 l = rng.integers(0, 256, (hh, ww), dtype=np.uint8); r = np.roll(l, -7, 1)
                 dl = torch.from_numpy(l).cuda(); dr = torch.from_numpy(r).cuda(); do = torch.zeros_like(dl)
                 ctx.compute_device(dl.data_ptr(), ww, dr.data_ptr(), ww, ww, hh, B, D, do.data_ptr(), ww, cuda_stream=torch.cuda.current_stream().cuda_stream, tuning=TUN)
