@@ -105,6 +105,9 @@ template <int HALF, int MODE> struct WsCfg {
     static constexpr int RB = HALF <= 4 ? 10 : WIN + 1;    // rows per batch = length of the register ring (> the window): 10, or 12 / 14 / 16 / 18
     static constexpr int NWW = RB / NRW;               // row-walker warps
     static constexpr int K = 12;                       // consumer warps
+    // consumers load the next row one row early: measured +7 % in the 2 x 9-group layout of block_size 11..15 (34.3 -> 31.9 us at
+    // B = 15, D = 32), -1..-4 % everywhere else (headline 70.3 -> 71.3 us; the 17-group instances spill)
+    static constexpr bool PFROW = HALF >= 5 && MODE == 2;
     static constexpr int NSLOT = NS * NGC;             // group slots of an H row
     // warp roles (6 warpgroups of 4 warps): producer class = warps 0..11, consumer class = warps 12..23
     static constexpr int W_AUX = NWW;                  // tail walker (the warp idles in the modes without a tail group)
@@ -234,13 +237,23 @@ __device__ __forceinline__ void ws_consume(const FastArgs& a, const uint2* __res
             const int batch = it - 1;
             const uint2* Hp = Hbase + (batch & 1) * HBUF;
             uint32_t* pkb = pkbase + (batch & 1) * PKBUF;
+            // PFROW: the loads of row rb + 1 are issued before the atomicMin of row rb (a shared-memory load cannot be hoisted over it)
+            uint2 nn[NG];
+#pragma unroll
+            for (int j = 0; j < NG; ++j) nn[j] = C::PFROW ? Hp[j * TWP] : make_uint2(0u, 0u);
 #pragma unroll
             for (int rb = 0; rb < RB; ++rb) {
                 uint32_t best = 0xFFFFFFFFu;
+                uint2 nc[NG];
+#pragma unroll
+                for (int j = 0; j < NG; ++j) {
+                    nc[j] = C::PFROW ? nn[j] : Hp[rb * HROW + j * TWP];
+                    if (C::PFROW && rb + 1 < RB) nn[j] = Hp[(rb + 1) * HROW + j * TWP];
+                }
 #pragma unroll
                 for (int j = 0; j < NG; ++j) {
                     // the slot of row rb was read for the last time one row ago (WIN < RB): the load lands in it directly
-                    const uint2 n = Hp[rb * HROW + j * TWP];
+                    const uint2 n = nc[j];
                     uint32_t kEl, kEh, kOl, kOh;
                     if (C::WIDE) {
                         // packed difference with the low lane biased by 0x8000: it never borrows from the high lane, so the

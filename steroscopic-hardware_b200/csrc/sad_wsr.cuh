@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __gr
     // a chunk none of whose disparities is a candidate anywhere in this strip (d > X-h, sad.go:64-67 + :212-218) contributes
     // nothing: chunk 0 always runs and writes every pixel
     if (g0 > 0 && min(x0 + C::CW, a.W) - 1 - HALF < 4 * g0) return;
+    const int nga = min(NGC, a.NG - g0);                                      // groups of this chunk that hold candidates at all
     const int r0 = yb0 - HALF;
     const int nb = ((yb1 - yb0) + 2 * HALF + RB - 1) / RB;
     const int xr0 = x0 - HALF - 3 - 4 * (g0 + NGC - 1) - C::OFF;              // image column of right-tile word 0 (multiple of 4)
@@ -197,9 +198,10 @@ __global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __gr
             else for (int it = 0; it < nb + 2; ++it) __syncthreads();
             return;
         }
+        // the last chunk of a range may hold fewer than NGC groups (max_disparity 256: 65 = 7 x 9 + 2): its walks fill fewer warps
         const int u = warp * 32 + lane;
-        const bool act = u < RB * NGC;
-        const int rb = act ? u / NGC : 0, gl = act ? u - rb * NGC : 0;
+        const bool act = u < RB * nga;
+        const int rb = act ? u / nga : 0, gl = act ? u - rb * nga : 0;
         const int nvalid = a.W - (x0 - HALF);                                 // steps of the walk inside the image
         const bool edge = nvalid < C::NSTEP;                                  // uniform: the strip touches x >= W
         const uint32_t one = opaque(a.k65536 >> 16), mone = opaque(0u - (a.k65536 >> 16));   // +1 / -1 in registers: adds on the FMA pipe
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __gr
         for (int k = 1; k < C::K; ++k)
             if (k == kB) grp = wsr_group(C::NWW, k);
         __syncthreads();
+        if (grp >= nga) grp = -1;
         if (grp < 0) {
             // the consumer warps without a group (one on each of the sub-partitions 0..2) finish a third of the rows each
             if (C::FIN3 && kB == 8) finisher(IC0{}, IC1{});
