@@ -41,6 +41,9 @@
 #ifndef WSR_FMAS
 #define WSR_FMAS 2
 #endif
+#ifndef WSR_NG2
+#define WSR_NG2 0       // 1 = two groups per consumer warp
+#endif
 #ifndef WSR_FIN3
 #define WSR_FIN3 0
 #endif
@@ -53,13 +56,26 @@
 
 namespace sadgpu {
 
-// Consumer warp k (sub-partition k % 4) -> disparity group of the chunk, or -1: with three walker warps sub-partition 3 takes three
-// groups and the others two; with four walker warps the groups are dealt round robin.
+// Consumer warp k (sub-partition k % 4) -> first disparity group of the chunk it owns (or -1) and how many.  One group per warp:
+// sub-partition 3 takes three groups and the others (which carry a walker) two.  WSR_NG2: two groups per warp where possible, so that
+// a consumer's chain is about as long as a walker's.
 __host__ __device__ constexpr int wsr_group(int nww, int k)
 {
     if (nww >= 4) return k < 9 ? k : -1;
+#if WSR_NG2
+    const int t[12] = {3, 5, 7, 0, -1, -1, -1, 2, -1, -1, -1, -1};
+#else
     const int t[12] = {3, 5, 7, 0, 4, 6, 8, 1, -1, -1, -1, 2};
+#endif
     return t[k];
+}
+__host__ __device__ constexpr int wsr_ngroups(int nww, int k)
+{
+#if WSR_NG2
+    return (nww < 4 && k <= 3) ? 2 : 1;
+#else
+    (void)nww; (void)k; return 1;
+#endif
 }
 
 template <int HALF> struct WsrCfg {
@@ -304,12 +320,13 @@ __global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __gr
     } else {
         // ======================= consumers: warp k owns group k for 32 columns =======================
         const int kB = warp - C::W_CONS;
-        int grp = wsr_group(C::NWW, 0);
+        int grp = wsr_group(C::NWW, 0), ngw = wsr_ngroups(C::NWW, 0);
 #pragma unroll
         for (int k = 1; k < C::K; ++k)
-            if (k == kB) grp = wsr_group(C::NWW, k);
+            if (k == kB) { grp = wsr_group(C::NWW, k); ngw = wsr_ngroups(C::NWW, k); }
         __syncthreads();
         if (grp >= nga) grp = -1;
+        else if (grp + ngw > nga) ngw = nga - grp;
         if (grp < 0) {
             // the consumer warps without a group (one on each of the sub-partitions 0..2) finish a third of the rows each
             if (C::FIN3 && kB == 8) finisher(IC0{}, IC1{});
@@ -319,59 +336,75 @@ __global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __gr
             return;
         }
         const int xB = x0 + lane;
-        const int dbase = 4 * (g0 + grp);
         const int dmax = min(a.D, xB - HALF);                 // largest evaluated disparity of this column (sad.go:64-67, :212-218)
-        // 32-bit sums: VE / VO are the RAW packed sums (low lane + 65536 * high lane, mod 2^32), V3 / V2 the high-lane sums alone;
-        // a never-evaluated candidate starts 2^22 above every real sum (245 055), so its key carries 2^31
-        uint32_t VE = dbase + 3 > dmax ? 1u << 22 : 0u, V3 = dbase + 1 > dmax ? 1u << 22 : 0u;
-        uint32_t VO = dbase + 2 > dmax ? 1u << 22 : 0u, V2 = dbase + 0 > dmax ? 1u << 22 : 0u;
         const uint32_t k512 = opaque(a.k65536 >> 7), m25 = opaque(0u - (a.k65536 << 9));    // keys sum*512 + d: 512 and -2^25
-        // the absolute disparities ride in the addends of the key multiply-adds (registers)
-        const uint32_t c3 = opaque((uint32_t)dbase + 3u), c1 = opaque((uint32_t)dbase + 1u), c2 = opaque((uint32_t)dbase + 2u), c0 = opaque((uint32_t)dbase);
         const uint2* Hbase = Hs + grp * TWP + lane;
         uint32_t* pkbase = pk + lane;
-        int sn = 0, so1 = C::NB - C::Q, so2 = C::NB - C::Q - 1;             // ring batch of the rows entering / leaving the window
-        for (int it = 0; it < nb + 2; ++it) {
-            if (it >= 1 && it <= nb && !(WSR_SKIP & 2)) {
-                const int batch = it - 1;
-                const uint2* Hn = Hbase + sn * RB * HROW;
-                const uint2* Ho1 = Hbase + so1 * RB * HROW;
-                const uint2* Ho2 = Hbase + so2 * RB * HROW;
-                uint32_t* pkb = pkbase + (batch & 1) * PKBUF;
-                // all loads of the batch first: a shared-memory load cannot be hoisted over the atomicMin of the row before it
-                uint2 n[RB], o[RB];
+        // NG groups (grp, grp + 1, ...) of this warp
+        auto consume = [&](auto ng_c) {
+            constexpr int NG = decltype(ng_c)::value;
+            constexpr int RH = NG == 1 ? RB : RB / 2;             // rows whose loads are issued together (register budget)
+            // 32-bit sums: VE / VO are the RAW packed sums (low lane + 65536 * high lane, mod 2^32), V3 / V2 the high-lane sums
+            // alone; a never-evaluated candidate starts 2^22 above every real sum (245 055), so its key carries 2^31
+            uint32_t VE[NG], V3[NG], VO[NG], V2[NG], c3[NG], c1[NG], c2[NG], c0[NG];
 #pragma unroll
-                for (int rb = 0; rb < RB; ++rb) {
-                    if (WSR_SKIP & 64) { n[rb] = make_uint2(it + rb, it); o[rb] = make_uint2(rb, 1); continue; }
-                    n[rb] = Hn[rb * HROW];
-                    o[rb] = rb >= C::M ? Ho1[(rb - C::M) * HROW] : Ho2[(rb - C::M + RB) * HROW];
-                }
-#pragma unroll
-                for (int rb = 0; rb < RB; ++rb) {
-                    // packed difference with the low lane biased by 0x8000: it never borrows from the high lane, so the arithmetic
-                    // shift yields the signed high-lane difference.  The copies are opaque so that the raw sum and the biased
-                    // difference stay ONE three-input add each (no shared n - o).
-                    if (WSR_SKIP & 32) { VE ^= n[rb].x ^ o[rb].x; VO ^= n[rb].y ^ o[rb].y; if (rb == RB - 1) pkb[0] = VE ^ VO; continue; }
-#if WSR_CONS == 1
-                    const uint32_t nx = n[rb].x, ny = n[rb].y;
-#else
-                    const uint32_t nx = opaque(n[rb].x), ny = opaque(n[rb].y);
-#endif
-                    const uint32_t dE = nx - o[rb].x + 0x8000u, dO = ny - o[rb].y + 0x8000u;
-                    VE = VE + n[rb].x - o[rb].x; V3 += (uint32_t)((int)dE >> 16);
-                    VO = VO + n[rb].y - o[rb].y; V2 += (uint32_t)((int)dO >> 16);
-                    const uint32_t kEl = VE * k512 + (V3 * m25 + c3), kEh = V3 * k512 + c1;
-                    const uint32_t kOl = VO * k512 + (V2 * m25 + c2), kOh = V2 * k512 + c0;
-                    if (WSR_SKIP & 16) pkb[rb * TW] = min(min(kEl, kEh), min(kOl, kOh));
-                    else
-                    atomicMin(pkb + rb * TW, min(min(kEl, kEh), min(kOl, kOh)));  // rows that are not output rows are filtered by the finisher
-                }
-                sn = sn + 1 == C::NB ? 0 : sn + 1;
-                so1 = so1 + 1 == C::NB ? 0 : so1 + 1;
-                so2 = so2 + 1 == C::NB ? 0 : so2 + 1;
+            for (int j = 0; j < NG; ++j) {
+                const int dbase = 4 * (g0 + grp + j);
+                VE[j] = dbase + 3 > dmax ? 1u << 22 : 0u; V3[j] = dbase + 1 > dmax ? 1u << 22 : 0u;
+                VO[j] = dbase + 2 > dmax ? 1u << 22 : 0u; V2[j] = dbase + 0 > dmax ? 1u << 22 : 0u;
+                // the absolute disparities ride in the addends of the key multiply-adds (registers)
+                c3[j] = opaque((uint32_t)dbase + 3u); c1[j] = opaque((uint32_t)dbase + 1u);
+                c2[j] = opaque((uint32_t)dbase + 2u); c0[j] = opaque((uint32_t)dbase);
             }
-            __syncthreads();
-        }
+            int sn = 0, so1 = C::NB - C::Q, so2 = C::NB - C::Q - 1;             // ring batch of the rows entering / leaving the window
+            for (int it = 0; it < nb + 2; ++it) {
+                if (it >= 1 && it <= nb && !(WSR_SKIP & 2)) {
+                    const int batch = it - 1;
+                    const uint2* Hn = Hbase + sn * RB * HROW;
+                    const uint2* Ho1 = Hbase + so1 * RB * HROW;
+                    const uint2* Ho2 = Hbase + so2 * RB * HROW;
+                    uint32_t* pkb = pkbase + (batch & 1) * PKBUF;
+#pragma unroll
+                    for (int rh = 0; rh < RB; rh += RH) {
+                        // all loads first: a shared-memory load cannot be hoisted over the atomicMin of the row before it
+                        uint2 n[RH][NG], o[RH][NG];
+#pragma unroll
+                        for (int r = 0; r < RH; ++r) {
+                            const int rb = rh + r;
+#pragma unroll
+                            for (int j = 0; j < NG; ++j) {
+                                n[r][j] = Hn[rb * HROW + j * TWP];
+                                o[r][j] = rb >= C::M ? Ho1[(rb - C::M) * HROW + j * TWP] : Ho2[(rb - C::M + RB) * HROW + j * TWP];
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < RH; ++r) {
+                            uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+                            for (int j = 0; j < NG; ++j) {
+                                // packed difference with the low lane biased by 0x8000: it never borrows from the high lane, so the
+                                // arithmetic shift yields the signed high-lane difference.  The copies are opaque so that the raw
+                                // sum and the biased difference stay ONE three-input add each (no shared n - o).
+                                const uint32_t nx = opaque(n[r][j].x), ny = opaque(n[r][j].y);
+                                const uint32_t dE = nx - o[r][j].x + 0x8000u, dO = ny - o[r][j].y + 0x8000u;
+                                VE[j] = VE[j] + n[r][j].x - o[r][j].x; V3[j] += (uint32_t)((int)dE >> 16);
+                                VO[j] = VO[j] + n[r][j].y - o[r][j].y; V2[j] += (uint32_t)((int)dO >> 16);
+                                const uint32_t kEl = VE[j] * k512 + (V3[j] * m25 + c3[j]), kEh = V3[j] * k512 + c1[j];
+                                const uint32_t kOl = VO[j] * k512 + (V2[j] * m25 + c2[j]), kOh = V2[j] * k512 + c0[j];
+                                best = min(best, min(min(kEl, kEh), min(kOl, kOh)));
+                            }
+                            atomicMin(pkb + (rh + r) * TW, best);  // rows that are not output rows are filtered by the finisher
+                        }
+                    }
+                    sn = sn + 1 == C::NB ? 0 : sn + 1;
+                    so1 = so1 + 1 == C::NB ? 0 : so1 + 1;
+                    so2 = so2 + 1 == C::NB ? 0 : so2 + 1;
+                }
+                __syncthreads();
+            }
+        };
+        if (ngw == 2) consume(std::integral_constant<int, 2>{});
+        else          consume(std::integral_constant<int, 1>{});
     }
 }
 
