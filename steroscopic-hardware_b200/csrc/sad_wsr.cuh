@@ -13,16 +13,16 @@
 //                 issues its shared-memory loads four steps early and does its running-sum adds on the FMA pipe;
 //   warp 3        finisher (key -> d*255/D LUT -> store, or the global key map when the disparity range is chunked);
 //   warp 7        TMA loader (cp.async.bulk.tensor.3d + mbarrier, zero fill outside the image) + replication of the left pixels;
-//   warps 8..19   consumers: nine of them own one group each for 32 columns (lanes = columns; three on sub-partition 3, two on each
-//                 of the sub-partitions that carry a walker): all 20 loads of the batch first (a shared-memory load cannot be
-//                 hoisted over the atomicMin of the row before), then 32-bit vertical running sums (raw packed sum + high-lane sum,
-//                 keys sum*512+d, as the h = 8 instance of sad_ws.cuh); the consumers of a pixel meet in one key through a
-//                 shared-memory atomicMin.
+//   warps 8..19   consumers: five of them own two groups (one) for 32 columns (lanes = columns; three groups on sub-partition 3, two
+//                 on each of the sub-partitions that carry a walker), so that a consumer's chain per batch is about as long as a
+//                 walker's: the loads of five rows first (a shared-memory load cannot be hoisted over the atomicMin of the row
+//                 before), then 32-bit vertical running sums (raw packed sum + high-lane sum, keys sum*512+d, as the h = 8
+//                 instance of sad_ws.cuh); the consumers of a pixel meet in one key through a shared-memory atomicMin.
 // Ring: NB = ceil(window / 10) + 2 batches of 10 rows; while the walkers write batch i the consumers read batch i-1 and the rows
 // window (= 10 q + m) rows older, which lie at compile-time offsets in batches i-1-q and i-2-q.  The ring starts zeroed: rows above
 // the band are the zero padding of the box filter.
 //
-// Measured (B200, 1080p, 8 frames per launch, profiles/r02_wsr_*): block 31: 39 / 78 / 265 us per frame at max_disparity 32 / 64 / 256
+// Measured (B200, 1080p, 8 frames per launch, profiles/r02_wsr_*): block 31: 39 / 75 / 252 us per frame at max_disparity 32 / 64 / 256
 // against 101 / 102 / 379 us for the mbarrier-pipelined ring kernel (sad_ring.cuh) it replaces as the planner's choice.  What was
 // tried and measured: batches of 14 rows on four walker warps (40 / 90 / 307 us: one sub-partition then carries a walker AND three
 // consumers), the finishing dealt to the three idle consumer warps (42 us: they sit on the walker sub-partitions), shared-memory
@@ -42,7 +42,7 @@
 #define WSR_FMAS 2
 #endif
 #ifndef WSR_NG2
-#define WSR_NG2 0       // 1 = two groups per consumer warp
+#define WSR_NG2 1       // 1 = two groups per consumer warp where possible (measured: D=64 78.2 -> 74.8 us, D=256 265.7 -> 252.2 us at block 31)
 #endif
 #ifndef WSR_FIN3
 #define WSR_FIN3 0
