@@ -49,6 +49,9 @@ constexpr bool dev_on(int half)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+// Row pitch of the shim's own device / pinned planes: a multiple of 16 bytes, so that TMA can address every frame that came through
+// a host entry point whatever its width (the planes are allocated for round_up(max_w, 256) bytes per row).
+inline int shim_pitch(int w) { return round_up(w, 16); }
 
 int validate(int w, int h, int B, int D, int y0, int y1)
 {
@@ -516,7 +519,7 @@ struct Slot {
     uint8_t *hL = nullptr, *hR = nullptr, *hOut = nullptr;     // pinned staging
     uint8_t *dL = nullptr, *dR = nullptr, *dOut = nullptr;     // device, pitched
     uint32_t* gkey = nullptr;
-    size_t pitch = 0;                                          // pitch of the frame in flight = round_up(w, 4): contiguous copies when the host stride matches
+    size_t pitch = 0;                                          // pitch of the frame in flight = shim_pitch(w): contiguous copies when the host stride matches
     std::mutex mu;
     bool busy = false;
     uint64_t seq = 0;
@@ -691,7 +694,7 @@ int submit_locked(sadgpu_ctx* c, Slot* s, const uint8_t* l, int ls, const uint8_
     if (rc) return rc;
     const int half = B / 2;
     const int ys = std::max(0, y0 - half), ye = std::min(h, y1 + half);
-    s->pitch = (size_t)round_up(w, 4);
+    s->pitch = (size_t)shim_pitch(w);
     s->dR = s->dL + s->pitch * (size_t)h;                      // right image directly behind the left one
     s->hR = s->hL + s->pitch * (size_t)h;
     const size_t img = s->pitch * (size_t)h;
@@ -959,7 +962,7 @@ int sadgpu_compute_region(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_t
                 Slot* s = e->slot;
                 e->l = l; e->r = r; e->ls = ls; e->rs = rs; e->w = w; e->h = h; e->B = B; e->D = D;
                 e->state = FrameEntry::STAGING; e->rc = 0; e->users = 1; e->served = 0; e->stale = attempt >= 3;
-                s->pitch = (size_t)round_up(w, 4);
+                s->pitch = (size_t)shim_pitch(w);
                 s->dR = s->dL + s->pitch * (size_t)h; s->hR = s->hL + s->pitch * (size_t)h;
                 e->nblocks = 2 * ceil_div(h, kStageRows);
                 e->done_blocks.store(0); e->next_block.store(0, std::memory_order_release);
@@ -1171,7 +1174,7 @@ int sadgpu_compute_nrgba(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, co
         if (e != cudaSuccess) return (int)e;
         s->rgba_bytes = 2 * plane;
     }
-    s->pitch = (size_t)round_up(w, 4);
+    s->pitch = (size_t)shim_pitch(w);
     s->dR = s->dL + s->pitch * (size_t)h;
     const uint8_t* src[2] = {l, r};
     const int stride[2] = {ls, rs};
@@ -1421,7 +1424,7 @@ int sadgpu_compute_checked(sadgpu_ctx* c, int stream, const uint8_t* l, int ls, 
     if (s->busy) return SADGPU_EBUSY;
     cudaError_t e = cudaSetDevice(s->device);
     if (e != cudaSuccess) return (int)e;
-    const size_t pitch = (size_t)round_up(w, 4), plane = pitch * (size_t)h;
+    const size_t pitch = (size_t)shim_pitch(w), plane = pitch * (size_t)h;
     if (s->post_bytes < 5 * plane) {
         cudaStreamSynchronize(s->st);
         cudaFree(s->dPost); s->dPost = nullptr; s->post_bytes = 0;
