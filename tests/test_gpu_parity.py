@@ -730,3 +730,36 @@ def test_post_processing_hooks_are_additive(torch_mod, ctx, oracle):
     got = ctx.compute_checked(L, R, 9, 64, tolerance=1, invalid_value=0)
     d12 = 12 * 255 // 64
     assert (got[10:-10, 90:190] == d12).mean() > 0.95
+
+
+def test_devices_from_environment(torch_mod, oracle, monkeypatch):
+    """sadgpu_create(devices = NULL): ordinals 0..n-1, or the first n entries of SADGPU_DEVICES (how the C++ mirror and the Go stub
+    pick their GPUs); a list that is too short or names a device that does not exist is an error, never a silent default."""
+    import ctypes
+    from despair import _native as N
+    L = N.lib()
+    rng = np.random.default_rng(8)
+    Limg, Rimg = synth_pair(rng, 40, 96, 1)
+    exp = oracle.frame_box(Limg, Rimg, 9, 64)
+
+    def create(n):
+        h = ctypes.c_void_p()
+        rc = L.sadgpu_create(None, n, 128, 64, 1, ctypes.byref(h))
+        return rc, h
+
+    last = torch_mod.cuda.device_count() - 1
+    for env in (None, "0", f"{last}", f" {last},0"):
+        if env is None:
+            monkeypatch.delenv("SADGPU_DEVICES", raising=False)
+        else:
+            monkeypatch.setenv("SADGPU_DEVICES", env)
+        rc, h = create(1)
+        assert rc == 0, (env, rc)
+        out = np.zeros_like(Limg)
+        N.check(L.sadgpu_compute(h, 0, Limg.ctypes.data, 96, Rimg.ctypes.data, 96, 96, 40, 9, 64, 0, 40, out.ctypes.data, 96))
+        L.sadgpu_destroy(h)
+        assert np.array_equal(out, exp), env
+    for env, n in (("0", 2), ("99", 1), ("-1", 1), ("x", 1)):
+        monkeypatch.setenv("SADGPU_DEVICES", env)
+        rc, h = create(n)
+        assert rc != 0, (env, n)
