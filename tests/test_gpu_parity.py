@@ -132,7 +132,7 @@ def test_shared_ring_warp_specialised_kernel(torch_mod, ctx, oracle, B):
     the strict flag, so that a silent substitution of another kernel would fail the test.  One chunk (D <= 32), chunked ranges,
     forced bands shorter than a batch / the window, every image kind."""
     rng = np.random.default_rng(700 + B)
-    for i, D in enumerate((16, 32, 36, 64, 100, 255, 256)):
+    for i, D in enumerate((16, 32, 36, 44, 48, 56, 60, 64, 100, 255, 256)):          # last chunk of 5, 9, 1, 3, 4, 6, 7, 8, 8, 1, 2 groups
         W = 16 * int(rng.integers(2, 24)); H = int(rng.integers(8, 90))
         L, R = synth_pair(rng, H, W, (i + B) % 5)
         tun = dict(STRICT_WSR)
@@ -532,6 +532,17 @@ def test_full_ui_grid_with_planner_defaults(torch_mod, ctx, oracle, B):
         W = int(rng.integers(180, 230)); H = int(rng.integers(56, 72))
         L, R = synth_pair(rng, H, W, (i + B) % 5)
         assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D), oracle.frame_box(L, R, B, D)), (W, H, B, D)
+
+
+@pytest.mark.parametrize("B", UI_BLOCKS)
+def test_full_ui_grid_through_the_host_entry_point(ctx, oracle, B):
+    """The same grid through sadgpu_compute (host buffers, odd widths): inside the library every plane has a 16-byte pitch, so the
+    TMA kernels — the planner's first choice at every point — run whatever the width."""
+    rng = np.random.default_rng(1900 + B)
+    for i, D in enumerate(UI_DISPARITIES):
+        W = int(rng.integers(150, 260)); H = int(rng.integers(40, 80))
+        L, R = synth_pair(rng, H, W, (i + B + 2) % 5)
+        assert np.array_equal(ctx.compute(L, R, B, D), oracle.frame_box(L, R, B, D)), (W, H, B, D)
 
 
 def _bands(h, chunk):
