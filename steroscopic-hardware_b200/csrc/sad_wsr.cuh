@@ -27,7 +27,9 @@
 // tried and measured: batches of 14 rows on four walker warps (40 / 90 / 307 us: one sub-partition then carries a walker AND three
 // consumers), the finishing dealt to the three idle consumer warps (42 us: they sit on the walker sub-partitions), shared-memory
 // stores instead of the atomicMin (no change), the consumer's adds as shared or separate three-input adds (no change), walker sums
-// on the ALU pipe (+2.5 %).  Role-isolation runs (WSR_SKIP): walkers alone 29 us, consumers alone 26 us, together 39 us — issue
+// on the ALU pipe (+2.5 %), the hand-over between the roles through named barriers (bar.arrive / bar.sync per batch and direction
+// instead of one __syncthreads: bit-exact, 2..8 % slower — the ring leaves the walkers one batch of slack either way), the walk's
+// running sum as difference-then-add (one dependent add per step: no change).  Role-isolation runs (WSR_SKIP): walkers alone 29 us, consumers alone 26 us, together 39 us — issue
 // slots 56 %, ALU pipe 64 %, shared-memory pipe 63 % of peak: no single resource binds, the kernel is short of independent warps
 // (one CTA per SM, 201 KB of shared memory).
 #pragma once
