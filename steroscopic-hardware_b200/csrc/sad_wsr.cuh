@@ -6,7 +6,8 @@
 // row that enters AND the row that leaves the window from the ring (one more LDS.64 per four evaluations), so it carries four
 // running sums per group and nothing else.
 //
-// A CTA owns one 32-column strip of a row band and one chunk of 9 disparity groups (36 disparity slots), 20 warps (warp w lives on
+// A CTA owns one 32-column strip of a row band and one chunk of 9 disparity groups (36 disparity slots; described below) or of 13
+// groups (52 slots, batches of 7 rows: the cheaper cover for 10..13, 37..39 and 64..65 groups), 20 warps (warp w lives on
 // sub-partition w % 4):
 //   warps 0..2    walkers: a batch is 10 rows x 9 groups = 90 (row, group) walks = the lanes of three warps.  A walk is 32 + 2h steps
 //                 (up to 62), keeps the 2h+1 old terms of both packed sums as SSA registers (setmaxnreg gives this warpgroup 120),
@@ -61,9 +62,12 @@ namespace sadgpu {
 // Consumer warp k (sub-partition k % 4) -> first disparity group of the chunk it owns (or -1) and how many.  One group per warp:
 // sub-partition 3 takes three groups and the others (which carry a walker) two.  WSR_NG2: two groups per warp where possible, so that
 // a consumer's chain is about as long as a walker's.
-__host__ __device__ constexpr int wsr_group(int nww, int k)
+__host__ __device__ constexpr int wsr_group(int ngc, int k)
 {
-    if (nww >= 4) return k < 9 ? k : -1;
+    if (ngc == 13) {                                    // 3 3 3 on the walker sub-partitions, 2 + 2 on sub-partition 3
+        const int t13[12] = {4, 7, 10, 0, -1, -1, -1, 2, -1, -1, -1, -1};
+        return t13[k];
+    }
 #if WSR_NG2
     const int t[12] = {3, 5, 7, 0, -1, -1, -1, 2, -1, -1, -1, -1};
 #else
@@ -71,20 +75,22 @@ __host__ __device__ constexpr int wsr_group(int nww, int k)
 #endif
     return t[k];
 }
-__host__ __device__ constexpr int wsr_ngroups(int nww, int k)
+__host__ __device__ constexpr int wsr_ngroups(int ngc, int k)
 {
+    if (ngc == 13) return k <= 2 ? 3 : 2;
 #if WSR_NG2
-    return (nww < 4 && k <= 3) ? 2 : 1;
+    return k <= 3 ? 2 : 1;
 #else
-    (void)nww; (void)k; return 1;
+    (void)k; return 1;
 #endif
 }
 
-template <int HALF> struct WsrCfg {
+template <int HALF, int NGC_ = 9> struct WsrCfg {
     static_assert(HALF >= 5 && HALF <= 15, "shared-memory-ring warp-specialised kernel: block_size 10..31");
     static constexpr int WIN = 2 * HALF + 1;
-    static constexpr int NGC = 9;                       // groups per chunk
-    static constexpr int RB = WSR_RB;                   // rows per batch: RB * NGC = 90 walker lanes = three warps
+    static_assert(NGC_ == 9 || NGC_ == 13, "chunks of 9 or 13 disparity groups");
+    static constexpr int NGC = NGC_;                    // groups per chunk
+    static constexpr int RB = NGC == 9 ? WSR_RB : 7;    // rows per batch: RB * NGC = 90 / 91 walker lanes = three warps
     static constexpr int TW = 32, TWP = 33, CW = 32;
     static constexpr int NSTEP = TW + 2 * HALF;
     static constexpr int NWW = (RB * NGC + 31) / 32;    // walker warps (warpgroup 0)
@@ -121,17 +127,17 @@ template <int HALF> struct WsrCfg {
     static constexpr int OFF_LUT = OFF_PK + 2 * PK_BYTES;
     static constexpr int OFF_MBAR = OFF_LUT + 1040;
     static constexpr int SMEM = OFF_MBAR + 64;
-    static_assert(M != 0 && NB > Q + 2, "ring geometry");
-    static_assert(RB * NGC <= 32 * NWW && NGC <= K, "walker lanes / consumer warps");
+    static_assert(M == 0 ? NB >= Q + 2 : NB > Q + 2, "ring geometry");
+    static_assert(RB * NGC <= 32 * NWW && NWW == 3, "walker lanes");
     static_assert(RWT * 4 <= 256 && LBOX <= 256, "TMA box");
     static_assert(128 * REGS_WALK + 128 * REGS_SERVICE + 384 * 96 <= NT * 96, "register budget");
     static_assert(SMEM <= 232448, "shared memory");
 };
 
-template <int HALF>
-__global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __grid_constant__ FastArgs a)
+template <int HALF, int NGC_>
+__global__ void __launch_bounds__(WsrCfg<HALF, NGC_>::NT, 1) sad_wsr_kernel(const __grid_constant__ FastArgs a)
 {
-    using C = WsrCfg<HALF>;
+    using C = WsrCfg<HALF, NGC_>;
     constexpr int TW = C::TW, TWP = C::TWP, RB = C::RB, NGC = C::NGC, WIN = C::WIN, HROW = C::HROW;
     extern __shared__ __align__(128) unsigned char smem[];
     uint2* Hs = reinterpret_cast<uint2*>(smem);                                   // [NR][NGC][TWP]
@@ -322,10 +328,10 @@ __global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __gr
     } else {
         // ======================= consumers: warp k owns group k for 32 columns =======================
         const int kB = warp - C::W_CONS;
-        int grp = wsr_group(C::NWW, 0), ngw = wsr_ngroups(C::NWW, 0);
+        int grp = wsr_group(NGC, 0), ngw = wsr_ngroups(NGC, 0);
 #pragma unroll
         for (int k = 1; k < C::K; ++k)
-            if (k == kB) { grp = wsr_group(C::NWW, k); ngw = wsr_ngroups(C::NWW, k); }
+            if (k == kB) { grp = wsr_group(NGC, k); ngw = wsr_ngroups(NGC, k); }
         __syncthreads();
         if (grp >= nga) grp = -1;
         else if (grp + ngw > nga) ngw = nga - grp;
@@ -345,7 +351,8 @@ __global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __gr
         // NG groups (grp, grp + 1, ...) of this warp
         auto consume = [&](auto ng_c) {
             constexpr int NG = decltype(ng_c)::value;
-            constexpr int RH = NG == 1 ? RB : RB / 2;             // rows whose loads are issued together (register budget)
+            // rows whose loads are issued together (register budget: 4 registers per row and group)
+            constexpr int RH = NG == 1 ? (RB < 12 ? RB : 9) : NG == 2 ? ((RB + 1) / 2 < 6 ? (RB + 1) / 2 : 6) : 4;
             // 32-bit sums: VE / VO are the RAW packed sums (low lane + 65536 * high lane, mod 2^32), V3 / V2 the high-lane sums
             // alone; a never-evaluated candidate starts 2^22 above every real sum (245 055), so its key carries 2^31
             uint32_t VE[NG], V3[NG], VO[NG], V2[NG], c3[NG], c1[NG], c2[NG], c0[NG];
@@ -373,6 +380,7 @@ __global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __gr
 #pragma unroll
                         for (int r = 0; r < RH; ++r) {
                             const int rb = rh + r;
+                            if (rb >= RB) continue;
 #pragma unroll
                             for (int j = 0; j < NG; ++j) {
                                 n[r][j] = Hn[rb * HROW + j * TWP];
@@ -381,6 +389,7 @@ __global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __gr
                         }
 #pragma unroll
                         for (int r = 0; r < RH; ++r) {
+                            if (rh + r >= RB) continue;
                             uint32_t best = 0xFFFFFFFFu;
 #pragma unroll
                             for (int j = 0; j < NG; ++j) {
@@ -405,7 +414,8 @@ __global__ void __launch_bounds__(WsrCfg<HALF>::NT, 1) sad_wsr_kernel(const __gr
                 __syncthreads();
             }
         };
-        if (ngw == 2) consume(std::integral_constant<int, 2>{});
+        if (NGC == 13 && ngw == 3) consume(std::integral_constant<int, 3>{});
+        else if (ngw == 2) consume(std::integral_constant<int, 2>{});
         else          consume(std::integral_constant<int, 1>{});
     }
 }

@@ -149,13 +149,13 @@ cudaError_t launch_ring(const FastPlan& p, cudaStream_t s)
     return cudaGetLastError();
 }
 
-template <int HALF>
+template <int HALF, int NGC>
 cudaError_t launch_wsr(const FastPlan& p, cudaStream_t s)
 {
-    using C = WsrCfg<HALF>;
+    using C = WsrCfg<HALF, NGC>;
     static_assert(C::SMEM <= kSmemBudget, "shared-memory-ring warp-specialised kernel does not fit shared memory");
     static std::atomic<unsigned long long> done{0};
-    auto k = sad_wsr_kernel<HALF>;
+    auto k = sad_wsr_kernel<HALF, NGC>;
     cudaError_t e = ensure_smem(k, C::SMEM, &done);
     if (e != cudaSuccess) return e;
     if (!p.a.use_tma) return cudaErrorInvalidValue;            // run_job re-plans onto another kernel when TMA cannot be used
@@ -188,10 +188,10 @@ template <int HALF> constexpr FastEntry ring_entry()
     else return kNoEntry;
 }
 
-template <int HALF> constexpr FastEntry wsr_entry()
+template <int HALF, int NGC> constexpr FastEntry wsr_entry()
 {
-    using C = WsrCfg<HALF>;
-    if constexpr (dev_on(HALF)) return FastEntry{launch_wsr<HALF>, C::NT, C::SMEM, C::RB, C::CW, C::NGC, C::LBOX, C::RWT * 4};
+    using C = WsrCfg<HALF, NGC>;
+    if constexpr (dev_on(HALF)) return FastEntry{launch_wsr<HALF, NGC>, C::NT, C::SMEM, C::RB, C::CW, C::NGC, C::LBOX, C::RWT * 4};
     else return kNoEntry;
 }
 
@@ -222,9 +222,12 @@ const FastEntry kWide[8] = {wide_entry<8>(), wide_entry<9>(), wide_entry<10>(), 
 const FastEntry kRing[11] = {ring_entry<5>(), ring_entry<6>(), ring_entry<7>(), ring_entry<8>(), ring_entry<9>(), ring_entry<10>(),
                              ring_entry<11>(), ring_entry<12>(), ring_entry<13>(), ring_entry<14>(), ring_entry<15>()};
 
-// warp-specialised kernel with a shared-memory ring (sad_wsr.cuh): h = 5..15, 32-column strips, chunks of 9 groups; needs TMA
-const FastEntry kWsr[11] = {wsr_entry<5>(), wsr_entry<6>(), wsr_entry<7>(), wsr_entry<8>(), wsr_entry<9>(), wsr_entry<10>(),
-                            wsr_entry<11>(), wsr_entry<12>(), wsr_entry<13>(), wsr_entry<14>(), wsr_entry<15>()};
+// warp-specialised kernel with a shared-memory ring (sad_wsr.cuh): h = 5..15, 32-column strips, chunks of 9 groups, and for
+// h >= 9 also of 13 groups (7-row batches); needs TMA
+#define WSR_ROW(H) {wsr_entry<H, 9>(), kNoEntry}
+#define WSR_ROW2(H) {wsr_entry<H, 9>(), wsr_entry<H, 13>()}
+const FastEntry kWsr[11][2] = {WSR_ROW(5), WSR_ROW(6), WSR_ROW(7), WSR_ROW(8), WSR_ROW2(9), WSR_ROW2(10), WSR_ROW2(11), WSR_ROW2(12),
+                               WSR_ROW2(13), WSR_ROW2(14), WSR_ROW2(15)};
 
 #ifdef SADGPU_DEV_VARIANTS
 template <int HALF>
@@ -257,6 +260,9 @@ bool fast_supported(int B) { return B / 2 <= 7; }
 bool wide_supported(int B) { return B / 2 >= 8 && B / 2 <= 15; }
 bool ws_supported(int B) { return B / 2 <= 8; }
 bool wsr_supported(int B) { return B / 2 >= 5 && B / 2 <= 15; }
+// relative cost of one pass of the shared-memory-ring kernel over a chunk of 9 / 13 groups (measured at block 21 and 31, 1080p:
+// 36.8..39.5 against 51.5..57.1 us for one chunk, 31.1..31.5 against 45.7..48.9 us per chunk of a chunked range)
+const int wsr_pass_cost[2] = {100, 150};
 
 // Planner default for block_size >= 10, from the measured variant sweep (profiles/r01_variant_sweep.json, inputs streaming
 // from HBM): a ring pass over 33 groups costs about 1.7x a pass of the phase-alternating kernel over 18 groups, a ring pass
@@ -319,10 +325,18 @@ int choose_kernel(int B, int D, const sadgpu_tuning* t, int* variant_out, int* m
         if (!ring_supported(B)) return SADGPU_EINVAL;
         fe = &kRing[half - 5];
         break;
-    case V_WSR:
+    case V_WSR: {
         if (!wsr_supported(B)) return SADGPU_EINVAL;
-        fe = &kWsr[half - 5];
+        // chunks of 9 or 13 groups: the cheaper cover of the range by the measured cost of a pass (wsr_pass_cost); 13 wins for
+        // 10..13, 37..39 and 65 groups (max_disparity 36..48, 144..152, 256)
+        int slot = 0;
+        if (gpc > 0) slot = gpc <= 9 ? 0 : 1;
+        else if (kWsr[half - 5][1].fn && wsr_pass_cost[1] * ((ng + 12) / 13) < wsr_pass_cost[0] * ((ng + 8) / 9)) slot = 1;
+        if (!kWsr[half - 5][slot].fn) slot = 0;
+        mode = slot;
+        fe = &kWsr[half - 5][slot];
         break;
+    }
 #ifdef SADGPU_DEV_VARIANTS
     case V_VH:
         if (!vh_supported(B)) return SADGPU_EINVAL;

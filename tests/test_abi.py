@@ -45,7 +45,8 @@ def test_plans_cover_the_parameter_surface(native):
             assert p["half"] == B // 2 and p["smem"] <= 232448 and p["NC"] * p["NGc"] >= p["NG"]
             assert p["grid"][0] * p["TW"] >= 1920
             if p["variant"] == "warp-specialised, shared-memory ring":
-                assert (B >= 18 or (B >= 16 and D <= 32)) and (p["NGc"], p["TW"], p["RB"]) == (9, 32, 10)
+                assert (B >= 18 or (B >= 16 and D <= 32)) and (p["NGc"], p["TW"], p["RB"]) in ((9, 32, 10), (13, 32, 7))
+                assert p["NGc"] == 9 or (B >= 18 and p["NG"] in (64, 65))             # 13-group chunks: D = 255, 256 among the D's of this loop
             elif p["variant"] == "warp-specialised":
                 if B <= 9:
                     assert (p["NGc"], p["TW"]) in ((33, 32), (17, 64), (9, 96), (5, 192))
@@ -60,7 +61,9 @@ def test_plans_cover_the_parameter_surface(native):
     assert despair.plan_describe(1920, 1080, 9, 16)["NGc"] == 5
     assert despair.plan_describe(1920, 1080, 15, 256)["variant"] == "warp-specialised"     # cfg2: four chunks of 17 groups
     assert despair.plan_describe(1920, 1080, 15, 68)["variant"] == "fast"
-    assert despair.plan_describe(1920, 1080, 31, 256)["variant"] == "warp-specialised, shared-memory ring"   # cfg4: eight chunks of 9 groups
+    assert despair.plan_describe(1920, 1080, 31, 256)["variant"] == "warp-specialised, shared-memory ring"   # cfg4: five chunks of 13 groups
+    assert (despair.plan_describe(1920, 1080, 31, 256)["NGc"], despair.plan_describe(1920, 1080, 31, 48)["NGc"]) == (13, 13)
+    assert (despair.plan_describe(1920, 1080, 31, 64)["NGc"], despair.plan_describe(1920, 1080, 31, 128)["NGc"]) == (9, 9)
     assert despair.plan_describe(1920, 1080, 31, 16)["variant"] == "warp-specialised, shared-memory ring"
     assert despair.plan_describe(1920, 1080, 16, 16)["variant"] == "warp-specialised, shared-memory ring"
     assert despair.plan_describe(1920, 1080, 31, 256, tuning=dict(kernel_variant=6))["variant"] == "ring"

@@ -138,6 +138,8 @@ def test_shared_ring_warp_specialised_kernel(torch_mod, ctx, oracle, B):
         tun = dict(STRICT_WSR)
         if i % 2:
             tun["band_rows"] = int(rng.integers(1, 40))
+        if B >= 18:
+            tun["groups_per_chunk"] = 9 if (i + B) % 2 else 13                 # both chunk sizes (9 groups x 10 rows, 13 groups x 7 rows)
         assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, tun), oracle.frame_box(L, R, B, D)), (W, H, B, D, tun)
 
 

@@ -9,6 +9,7 @@ if os.environ.get("SADGPU_LIB"): N.LIB_PATH = os.environ["SADGPU_LIB"]
 import despair
 BS = [int(x) for x in os.environ.get("BS", os.environ.get("B", "9")).split(",")]; DS = [int(x) for x in os.environ.get("DS", "128,64,32,16").split(",")]
 VAR = int(os.environ.get("VARIANT", 0)); TUN = dict(kernel_variant=VAR) if VAR else None
+if os.environ.get("GPC"): TUN = dict(TUN or {}, groups_per_chunk=int(os.environ["GPC"]))
 W, H, F = 1920, 1080, 8
 ctx = despair.Context([0], W, H, 1)
 rng = np.random.default_rng(1)
