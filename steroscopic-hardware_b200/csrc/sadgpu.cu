@@ -436,75 +436,100 @@ bool make_tmap(CUtensorMap* m, const uint8_t* base, int w, int h, size_t pitch, 
 // megabytes per frame; a few helper threads cut them to a fraction.  The pool is created with the context.
 class CopyPool {
 public:
-    explicit CopyPool(int helpers)
+    explicit CopyPool(int helpers) : w_(helpers > 0 ? new Worker[helpers] : nullptr), n_(helpers)
     {
-        for (int i = 0; i < helpers; ++i) th_.emplace_back([this] { run(); });
+        for (int i = 0; i < n_; ++i) w_[i].th = std::thread([this, i] { run(w_[i]); });
     }
     ~CopyPool()
     {
-        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
-        cv_.notify_all();
-        for (auto& t : th_) t.join();
+        stop_.store(true);
+        for (int i = 0; i < n_; ++i) {
+            { std::lock_guard<std::mutex> g(w_[i].m); }
+            w_[i].cv.notify_all();
+            w_[i].th.join();
+        }
+        delete[] w_;
     }
-    // rows x width bytes, row pitches dp / sp; contiguous when dp == sp == width.  Small copies stay on the caller.
+    // rows x width bytes, row pitches dp / sp; contiguous when dp == sp == width.  Copies of 512 KB and more are shared with the
+    // helpers that are idle right now (a helper that another caller holds is simply not used); small copies stay on the caller.
     void copy(uint8_t* dst, size_t dp, const uint8_t* src, size_t sp, size_t width, size_t rows)
     {
         if (rows == 0 || width == 0) return;
         const bool contig = dp == width && sp == width;
         const size_t total = width * rows;
-        // waking a sleeping helper costs tens of microseconds on this class of host: only copies of 4 MB and more are split
-        // (measured: 1080p planes got slower when split three ways, 4K planes 20 % faster)
-        const int parts = total < (4u << 20) ? 1 : (int)std::min<size_t>(th_.size() + 1, total / (2u << 20));
-        if (parts <= 1) { one(dst, dp, src, sp, width, rows, contig); return; }
-        Latch latch{parts - 1};
+        const int want = total < (512u << 10) ? 0 : (int)std::min<size_t>((size_t)n_, total / (256u << 10) - 1);
+        Worker* got[8];
+        int ngot = 0;
+        for (int i = 0; i < n_ && ngot < want && ngot < 8; ++i) {
+            int idle = IDLE;
+            if (w_[i].state.compare_exchange_strong(idle, CLAIMED)) got[ngot++] = &w_[i];
+        }
+        if (ngot == 0) { one(dst, dp, src, sp, width, rows, contig); return; }
+        const int parts = ngot + 1;
+        std::atomic<int> latch{ngot};                       // lives on this stack: a helper's last access is the decrement
         for (int p = 1; p < parts; ++p) {
-            const size_t r0 = rows * p / parts, r1 = rows * (p + 1) / parts;
-            const size_t b0 = total * p / parts, b1 = total * (p + 1) / parts;
-            push([=, &latch] {
-                if (contig) memcpy(dst + b0, src + b0, b1 - b0);
-                else one(dst + r0 * dp, dp, src + r0 * sp, sp, width, r1 - r0, false);
-                latch.done();
-            });
+            Worker& w = *got[p - 1];
+            if (contig) {
+                const size_t b0 = total * p / parts, b1 = total * (p + 1) / parts;
+                w.task = Task{dst + b0, src + b0, b1 - b0, b1 - b0, b1 - b0, 1, true};
+            } else {
+                const size_t r0 = rows * p / parts, r1 = rows * (p + 1) / parts;
+                w.task = Task{dst + r0 * dp, src + r0 * sp, dp, sp, width, r1 - r0, false};
+            }
+            w.latch = &latch;
+            w.state.store(READY);                            // seq_cst: ordered against the helper's `asleep` flag
+            if (w.asleep.load()) { { std::lock_guard<std::mutex> g(w.m); } w.cv.notify_one(); }
         }
         if (contig) memcpy(dst, src, total / parts);
         else one(dst, dp, src, sp, width, rows / parts, false);
-        latch.wait();
+        for (int spin = 0; latch.load(std::memory_order_acquire) > 0; ++spin)
+            if (spin > 2000) std::this_thread::yield();
     }
 private:
-    struct Latch {                      // lives on the caller's stack: the worker's last access is the decrement
-        std::atomic<int> n;
-        explicit Latch(int k) : n(k) {}
-        void done() { n.fetch_sub(1, std::memory_order_release); }
-        void wait() { while (n.load(std::memory_order_acquire) > 0) std::this_thread::yield(); }   // tens of microseconds
+    enum { IDLE = 0, CLAIMED = 1, READY = 2 };
+    struct Task { uint8_t* dst; const uint8_t* src; size_t dp, sp, width, rows; bool contig; };
+    struct alignas(64) Worker {
+        std::atomic<int> state{IDLE};
+        std::atomic<bool> asleep{false};
+        Task task{};
+        std::atomic<int>* latch = nullptr;
+        std::mutex m;
+        std::condition_variable cv;
+        std::thread th;
     };
     static void one(uint8_t* dst, size_t dp, const uint8_t* src, size_t sp, size_t width, size_t rows, bool contig)
     {
         if (contig) { memcpy(dst, src, width * rows); return; }
         for (size_t y = 0; y < rows; ++y) memcpy(dst + y * dp, src + y * sp, width);
     }
-    void push(std::function<void()> f)
-    {
-        { std::lock_guard<std::mutex> g(m_); q_.push_back(std::move(f)); }
-        cv_.notify_one();
-    }
-    void run()
+    // A helper polls its mailbox for a while after each task (a frame is several copies a few hundred microseconds apart; waking a
+    // sleeping thread costs tens of microseconds on the GPU hosts), then sleeps.
+    void run(Worker& w)
     {
         for (;;) {
-            std::function<void()> f;
-            {
-                std::unique_lock<std::mutex> l(m_);
-                cv_.wait(l, [&] { return stop_ || !q_.empty(); });
-                if (q_.empty()) return;
-                f = std::move(q_.front()); q_.erase(q_.begin());
+            bool ready = false;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (int spin = 0; !ready && !stop_.load(std::memory_order_relaxed); ++spin) {
+                ready = w.state.load(std::memory_order_acquire) == READY;
+                if (!ready && (spin & 255) == 255 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) break;
             }
-            f();
+            if (!ready) {
+                std::unique_lock<std::mutex> l(w.m);
+                w.asleep.store(true);
+                w.cv.wait(l, [&] { return stop_.load() || w.state.load() == READY; });
+                w.asleep.store(false);
+                if (w.state.load() != READY) return;           // stop
+            }
+            const Task t = w.task;
+            std::atomic<int>* latch = w.latch;
+            one(t.dst, t.dp, t.src, t.sp, t.width, t.rows, t.contig);
+            w.state.store(IDLE, std::memory_order_release);
+            latch->fetch_sub(1, std::memory_order_release);
         }
     }
-    std::vector<std::thread> th_;
-    std::vector<std::function<void()>> q_;
-    std::mutex m_;
-    std::condition_variable cv_;
-    bool stop_ = false;
+    Worker* w_;
+    int n_;
+    std::atomic<bool> stop_{false};
 };
 
 // A few dozen nanoseconds of critical section, taken ~300 times per frame by up to 32 threads: a contended std::mutex costs a
