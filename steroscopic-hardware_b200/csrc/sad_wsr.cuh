@@ -48,13 +48,10 @@
 #define WSR_NG2 1       // 1 = two groups per consumer warp where possible (measured: D=64 78.2 -> 74.8 us, D=256 265.7 -> 252.2 us at block 31)
 #endif
 #ifndef WSR_FIN3
-#define WSR_FIN3 0
-#endif
-#ifndef WSR_CONS
-#define WSR_CONS 0
+#define WSR_FIN3 0      // 1 = the finishing is dealt to the three consumer warps without a group (measured slower)
 #endif
 #ifndef WSR_SKIP
-#define WSR_SKIP 0      // developer timing experiments (results wrong): 1 = walkers idle, 2 = consumers idle, 8 = finisher idle
+#define WSR_SKIP 0      // developer timing experiments (results wrong): 1 = walkers idle, 2 = consumers idle, 8 = finisher idle, 128 = no tile loads
 #endif
 
 namespace sadgpu {
