@@ -651,7 +651,7 @@ int run_job(sadgpu_ctx* c, int dev_index, const Job& j, const sadgpu_tuning* t, 
         sadgpu_tuning t2{};
         if (t) t2 = *t;
         // what the planner chose before this kernel existed: ring or wide by the measured pass costs
-        t2.kernel_variant = ring_auto(j.B, j.D) ? V_RING : V_WIDE; t2.groups_per_chunk = 0;
+        t2.kernel_variant = ring_auto(j.B, j.D) ? V_RING : fast_supported(j.B) ? V_FAST : V_WIDE; t2.groups_per_chunk = 0;
         if ((rc = make_fast_plan(j.w, j.h, j.B, j.D, j.y0, j.y1, j.n_frames, &t2, c->sm_count[dev_index], &p))) return rc;
     }
     const FastEntry* fe = p.fe;

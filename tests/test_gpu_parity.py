@@ -167,7 +167,7 @@ def test_shared_ring_kernel_row_ranges_frames_and_fallback(torch_mod, ctx, oracl
     L, R = synth_pair(rng, 40, 131, 0)
     with pytest.raises(despair.SadGpuError):
         dev_run(torch_mod, ctx, L, R, 31, 64, STRICT_WSR)
-    for (B, D) in ((31, 64), (19, 16), (16, 32)):
+    for (B, D) in ((31, 64), (19, 16), (16, 32), (13, 16), (11, 128), (15, 68)):      # ring, wide and (block <= 15) phase-alternating fallbacks
         assert np.array_equal(dev_run(torch_mod, ctx, L, R, B, D, dict(kernel_variant=7)), oracle.frame_box(L, R, B, D)), (B, D)
 
 
