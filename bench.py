@@ -153,13 +153,13 @@ def extra_single_gpu_configs(torch, despair, O, device_index):
         n = 16
         dL = torch.from_numpy(L).cuda().unsqueeze(0).repeat(n, 1, 1).contiguous(); dR = torch.from_numpy(R).cuda().unsqueeze(0).repeat(n, 1, 1).contiguous()
         dO = torch.zeros_like(dL)
-        us = time_device_batch(torch, ctx, dL, dR, dO, 3840, 2160, 31, 256, 2, 2)
+        us = time_device_batch(torch, ctx, dL, dR, dO, 3840, 2160, 31, 256, 8, 2)
         rows = dO[n - 1, 1000:1016].cpu().numpy()
         ok = np.array_equal(rows, O.frame_box(L, R, 31, 256, 1000, 1016))
         out["cfg4_one_gpu"] = {"workload": "synthetic 3840x2160, block 31, max disparity 256, device-resident", "us_per_frame": us,
-                               "frames_per_sec": 1e6 / us, "frac": frac_of_roofline(3840, 2160, 256, us), "frames_per_launch": 2,
+                               "frames_per_sec": 1e6 / us, "frac": frac_of_roofline(3840, 2160, 256, us), "frames_per_launch": 8,
                                "parity": bool(ok), "parity_against": "oracle rows 1000..1015",
-                               "plan": despair.plan_describe(3840, 2160, 31, 256, frames=2)}
+                               "plan": despair.plan_describe(3840, 2160, 31, 256, frames=8)}
         del dL, dR, dO
         torch.cuda.empty_cache()
     finally:

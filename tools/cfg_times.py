@@ -36,7 +36,7 @@ def main():
     ctx = despair.Context([0], 3840, 2160, 1)
     out = {"configs": [], "sweep": []}
     for name, (W, H, B, D, F) in {"cfg1 640x480 B9 D64": (640, 480, 9, 64, 64), "cfg2 1080p B15 D256": (1920, 1080, 15, 256, 16),
-                                  "cfg3 1080p B9 D128": (1920, 1080, 9, 128, 16), "cfg4 4K B31 D256 (one GPU)": (3840, 2160, 31, 256, 2)}.items():
+                                  "cfg3 1080p B9 D128": (1920, 1080, 9, 128, 16), "cfg4 4K B31 D256 (one GPU)": (3840, 2160, 31, 256, 8)}.items():
         r = time_cfg(ctx, W, H, B, D, F); r["name"] = name; out["configs"].append(r); print(r, flush=True)
     if "--sweep" in sys.argv:
         for B in (3, 5, 7, 9, 11, 13, 15, 16, 17, 21, 25, 31):
