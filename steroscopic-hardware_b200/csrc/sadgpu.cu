@@ -598,6 +598,7 @@ struct sadgpu_ctx {
     std::vector<FrameEntry*> cache;
     uint64_t cache_tick = 0;
     std::atomic<long long> region_calls{0}, region_frames{0}, region_stale{0};
+    std::atomic<uint64_t> verify_clock{1};  // orders chunk calls and snapshot verifications (rows_match_snapshot)
 };
 
 namespace {
@@ -863,6 +864,10 @@ struct FrameEntry {
     bool stale = false;                                        // a caller's pixels differed from the snapshot: no new caller may attach
     int nblocks = 0;
     std::atomic<int> next_block{0}, done_blocks{0};
+    // per plane and block of kVerifyRows rows: (clock at the start of the latest comparison with the snapshot) << 2 | differs << 1 | done
+    std::atomic<uint64_t>* vstate = nullptr;
+    int vblocks = 0;                                           // blocks per plane
+    ~FrameEntry() { delete[] vstate; }
 };
 
 void stage_blocks(sadgpu_ctx*, FrameEntry* e, const uint8_t* l, const uint8_t* r)
@@ -899,18 +904,45 @@ int produce_frame(sadgpu_ctx* c, FrameEntry* e)
     return err == cudaSuccess ? SADGPU_OK : (int)err;
 }
 
-bool rows_match_snapshot(const FrameEntry* e, const uint8_t* l, const uint8_t* r, int ya, int yb)
+// Do the caller's rows [ya, yb) still equal the snapshot the entry was computed from?  Compared in blocks of kVerifyRows rows, and a
+// block that another chunk call compared AFTER this call began (`ticket` was drawn from the same clock at its start) is not
+// compared again: the images may not change during a call, so what held at any moment of it holds for it.  Neighbouring chunks
+// overlap by 2h rows (three times a chunk's own rows for the 8-row bands of a 1080p frame), which made these comparisons 30 % of
+// the OutputCamera call pattern.  Blocks are supersets of [ya, yb): a difference outside the rows that matter only costs a recompute.
+constexpr int kVerifyRows = 8;
+bool rows_match_snapshot(sadgpu_ctx* c, FrameEntry* e, const uint8_t* l, const uint8_t* r, int ya, int yb, uint64_t ticket)
 {
+#ifdef SADGPU_DEV_NOVERIFY
+    return true;                                     // developer timing experiment only: UNSAFE
+#endif
     const Slot* s = e->slot;
+    const int b0 = ya / kVerifyRows, b1 = (yb - 1) / kVerifyRows;
     for (int plane = 0; plane < 2; ++plane) {
         const uint8_t* src = plane ? r : l;
         const size_t sp = (size_t)(plane ? e->rs : e->ls);
         const uint8_t* snap = plane ? s->hR : s->hL;
-        if (sp == s->pitch && s->pitch == (size_t)e->w) {
-            if (memcmp(src + (size_t)ya * sp, snap + (size_t)ya * s->pitch, (size_t)(yb - ya) * e->w)) return false;
-        } else {
-            for (int y = ya; y < yb; ++y)
-                if (memcmp(src + (size_t)y * sp, snap + (size_t)y * s->pitch, (size_t)e->w)) return false;
+        for (int b = b0; b <= b1; ++b) {
+            std::atomic<uint64_t>& st = e->vstate[plane * e->vblocks + b];
+            for (;;) {
+                uint64_t v = st.load(std::memory_order_acquire);
+                if ((v >> 2) >= ticket) {                          // compared (or being compared) after this call began
+                    if (v & 1) { if (v & 2) return false; break; }
+#if defined(__x86_64__) || defined(__i386__)
+                    __builtin_ia32_pause();
+#endif
+                    continue;
+                }
+                const uint64_t now = c->verify_clock.fetch_add(1, std::memory_order_acq_rel);
+                if (!st.compare_exchange_strong(v, now << 2, std::memory_order_acq_rel)) continue;
+                const int r0 = b * kVerifyRows, r1 = std::min(e->h, r0 + kVerifyRows);
+                bool same = true;
+                if (sp == s->pitch && s->pitch == (size_t)e->w) same = memcmp(src + (size_t)r0 * sp, snap + (size_t)r0 * s->pitch, (size_t)(r1 - r0) * e->w) == 0;
+                else
+                    for (int y = r0; y < r1 && same; ++y) same = memcmp(src + (size_t)y * sp, snap + (size_t)y * s->pitch, (size_t)e->w) == 0;
+                st.store((now << 2) | (same ? 1u : 3u), std::memory_order_release);
+                if (!same) return false;
+                break;
+            }
         }
     }
     return true;
@@ -941,6 +973,10 @@ int new_cache_entry(sadgpu_ctx* c, FrameEntry** out)
     if (err == cudaSuccess) err = alloc_slot_buffers(s, c->max_w, c->max_h, 1);
     if (err != cudaSuccess) { free_slot(s); delete e; return (int)err; }
     e->slot = s;
+    e->vblocks = ceil_div(c->max_h, kVerifyRows);
+    e->vstate = new (std::nothrow) std::atomic<uint64_t>[2 * (size_t)e->vblocks];
+    if (!e->vstate) { free_slot(s); delete e; return SADGPU_ENOMEM; }
+    for (int i = 0; i < 2 * e->vblocks; ++i) e->vstate[i].store(0, std::memory_order_relaxed);
     *out = e;
     return SADGPU_OK;
 }
@@ -969,6 +1005,7 @@ int sadgpu_compute_region(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_t
     });
     if (c->cache.empty()) return c->cache_rc ? c->cache_rc : SADGPU_ENOMEM;
     const int half = B / 2;
+    const uint64_t ticket = c->verify_clock.fetch_add(1, std::memory_order_acq_rel);      // this call began here
     for (int attempt = 0;; ++attempt) {
         FrameEntry* e = nullptr;
         bool producer = false;
@@ -1001,6 +1038,7 @@ int sadgpu_compute_region(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_t
                 Slot* s = e->slot;
                 e->l = l; e->r = r; e->ls = ls; e->rs = rs; e->w = w; e->h = h; e->B = B; e->D = D;
                 e->state = FrameEntry::STAGING; e->rc = 0; e->users = 1; e->served = 0; e->stale = attempt >= 3;
+                for (int i = 0; i < 2 * e->vblocks; ++i) e->vstate[i].store(0, std::memory_order_relaxed);      // no comparison with this snapshot yet
                 s->pitch = (size_t)shim_pitch(w);
                 s->dR = s->dL + s->pitch * (size_t)h; s->hR = s->hL + s->pitch * (size_t)h;
                 e->nblocks = 2 * ceil_div(h, kStageRows);
@@ -1050,7 +1088,7 @@ int sadgpu_compute_region(sadgpu_ctx* c, const uint8_t* l, int ls, const uint8_t
             };
             wait_for([&] { return e->state.load(std::memory_order_acquire) != FrameEntry::STAGING; });
             bool same = true;
-            if (e->state.load(std::memory_order_acquire) != FrameEntry::FAILED) same = rows_match_snapshot(e, l, r, ya, yb);
+            if (e->state.load(std::memory_order_acquire) != FrameEntry::FAILED) same = rows_match_snapshot(c, e, l, r, ya, yb, ticket);
             if (same) wait_for([&] { const int st = e->state.load(std::memory_order_acquire); return st == FrameEntry::READY || st == FrameEntry::FAILED; });
             { std::lock_guard<SpinLock> g(c->cache_mu); state = e->state; rc = e->rc; if (!same) e->stale = true; }
             if (!same) {
