@@ -776,3 +776,29 @@ def test_devices_from_environment(torch_mod, oracle, monkeypatch):
         monkeypatch.setenv("SADGPU_DEVICES", env)
         rc, h = create(n)
         assert rc != 0, (env, n)
+
+
+def test_concurrent_pageable_calls_share_the_staging_helpers(ctx, oracle):
+    """Four threads, each on its own stream slot, call sadgpu_compute on pageable 1080p planes at the same time: the staging copies
+    (>= 512 KB) are shared with whichever helper threads are idle at that moment, a helper another caller holds is not used."""
+    import threading
+    rng = np.random.default_rng(44)
+    H, W, B, D = 1080, 1920, 9, 128
+    pairs = [synth_pair(rng, H, W, 1) for _ in range(4)]
+    exps = [oracle.frame_box(L, R, B, D, 500, 516) for L, R in pairs]
+    errors = []
+
+    def worker(k):
+        try:
+            out = np.zeros((H, W), np.uint8)
+            for it in range(6):
+                L, R = pairs[(k + it) % 4]
+                ctx.compute(L, R, B, D, stream=k, out=out)
+                if not np.array_equal(out[500:516], exps[(k + it) % 4]):
+                    errors.append((k, it))
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not errors, errors
